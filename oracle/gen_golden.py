@@ -1,0 +1,243 @@
+"""
+Generate the golden fixtures under tests/golden/ by running the REAL reference (imported from
+/root/reference, read-only) in the build container.  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/gen_golden.py
+
+The reference is Python and cannot travel to the GPU box, so its outputs are committed as small
+.npz fixtures; weights are NOT stored -- they are regenerated from `monoloco_b200.synthetic`
+seeds (numpy RandomState, machine independent) and a checksum is stored instead.
+
+matplotlib is absent here; the reference imports pyplot at module import (net.py:19 ->
+activity.py:10, losses.py:12), so it is stubbed with MagicMock before import.
+"""
+import json
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+OUT = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+
+for _m in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.patches', 'matplotlib.cm']:
+    sys.modules[_m] = MagicMock()
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+from monoloco.network import Loco  # noqa: E402
+from monoloco.network.architectures import LocoModel, MonolocoModel  # noqa: E402
+from monoloco.network.process import (preprocess_monoloco, preprocess_monstereo, extract_outputs,  # noqa: E402
+                                      extract_outputs_mono, cluster_outputs, filter_outputs,
+                                      preprocess_pifpaf, laplace_sampling, unnormalize_bi)
+from monoloco.utils import xyz_from_distance, pixel_to_camera, get_keypoints  # noqa: E402
+from monoloco.train.losses import CompositeLoss, MultiTaskLoss, AutoTuneMultiTaskLoss  # noqa: E402
+
+from monoloco_b200 import synthetic  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def sd_to_torch(sd):
+    return {k: torch.from_numpy(np.array(v)) for k, v in sd.items()}
+
+
+def sd_checksum(sd):
+    return float(sum(float(np.asarray(v, dtype=np.float64).sum()) for k, v in sorted(sd.items())))
+
+
+def build(kind, input_size, output_size, linear_size, num_stage, seed, p_dropout=0.2):
+    sd = synthetic.make_state_dict(kind, input_size, output_size, linear_size, num_stage, seed)
+    if kind == 'loco':
+        m = LocoModel(input_size, output_size, linear_size, p_dropout, num_stage, device='cpu')
+    else:
+        m = MonolocoModel(input_size, output_size, linear_size, p_dropout, num_stage)
+    m.load_state_dict(sd_to_torch(sd))
+    m.eval()
+    return m, sd
+
+
+def dic_to_np(dic, prefix=''):
+    out = {}
+    for k, v in dic.items():
+        if k == 'yaw':
+            out[prefix + 'yaw_pred'] = v[0].numpy()
+            out[prefix + 'yaw_orig'] = v[1].numpy()
+        elif k == 'epi':
+            out[prefix + 'epi'] = np.asarray(v, dtype=np.float32)
+        else:
+            out[prefix + k] = v.numpy()
+    return out
+
+
+def kat_preprocess():
+    """Known-answer fixtures of the reference's own tests: stored X == preprocess(kps, K)."""
+    for mode in ('mono', 'stereo'):
+        d = json.load(open(os.path.join(REF, 'tests', 'sample_joints-kitti-%s.json' % mode)))
+        for phase in ('train', 'val'):
+            kps = np.asarray(d[phase]['kps'], dtype=np.float32)[:, 0]  # (N,3,17|34)
+            xs = np.asarray(d[phase]['X'], dtype=np.float32)
+            ys = np.asarray(d[phase]['Y'], dtype=np.float32)
+            ks = []
+            for k in d[phase]['K']:
+                if k not in ks:
+                    ks.append(k)
+            k_rows = np.zeros((kps.shape[0], 3, 3), dtype=np.float32)
+            worst = 0.0
+            for i in range(kps.shape[0]):
+                best = None
+                for k in ks:
+                    kt = torch.tensor(k)
+                    if mode == 'mono':
+                        x = preprocess_monoloco(torch.from_numpy(kps[i:i + 1]), kt)[0].numpy()
+                    else:
+                        le = preprocess_monoloco(torch.from_numpy(kps[i:i + 1, :, :17]), kt)[0]
+                        ri = preprocess_monoloco(torch.from_numpy(kps[i:i + 1, :, 17:]), kt)[0]
+                        x = torch.cat((le, le - ri)).numpy()  # prep/preprocess_kitti.py:244-247
+                    err = float(np.abs(x - xs[i]).max())
+                    if best is None or err < best[0]:
+                        best = (err, k)
+                k_rows[i] = np.asarray(best[1], dtype=np.float32)
+                worst = max(worst, best[0])
+            print('kat', mode, phase, kps.shape, 'max |X - preprocess(kps,K)| =', worst)
+            assert worst < 2e-6
+            np.savez_compressed(os.path.join(OUT, 'kat_%s_%s.npz' % (mode, phase)), kps=kps, K=k_rows, X=xs, Y=ys)
+
+
+def ref_forward():
+    cfgs = [
+        # name, kind, in, out, L, stages, seed, n_rows
+        ('loco_mono_l128', 'loco', 34, 9, 128, 3, 11, 77),
+        ('loco_stereo_l128', 'loco', 68, 10, 128, 3, 12, 77),
+        ('loco_mono_l256_s2', 'loco', 34, 9, 256, 2, 13, 41),
+        ('monoloco_l256_o2', 'monoloco', 34, 2, 256, 3, 14, 50),
+        ('monoloco_l128_o9', 'monoloco', 34, 9, 128, 3, 15, 50),
+        ('loco_mono_l1024', 'loco', 34, 9, 1024, 3, 1, 169),
+        ('loco_stereo_l1024', 'loco', 68, 10, 1024, 3, 2, 96),
+        ('monoloco_l1024_o9', 'monoloco', 34, 9, 1024, 3, 3, 96),
+    ]
+    kat = np.load(os.path.join(OUT, 'kat_mono_val.npz'))
+    for name, kind, isz, osz, L, st, seed, n in cfgs:
+        model, sd = build(kind, isz, osz, L, st, seed)
+        if name == 'loco_mono_l1024':
+            x = kat['X'][:n]  # BASELINE config 1: the reference fixture's val rows
+        else:
+            x = synthetic.make_inputs(n, isz, seed=100 + seed)
+        with torch.no_grad():
+            out = model(torch.from_numpy(x))
+        save = dict(x=x, out=out.numpy(), cfg=np.array([isz, osz, L, st, seed]), kind=kind,
+                    checksum=sd_checksum(sd))
+        if kind == 'loco' or osz == 9:
+            dec = extract_outputs(out) if kind == 'loco' else extract_outputs_mono(out)
+            save.update(dic_to_np(dec, 'dec_'))
+        np.savez_compressed(os.path.join(OUT, 'ref_fwd_%s.npz' % name), **save)
+        print('fwd', name, out.shape, float(out.abs().mean()))
+
+
+def ref_loco_forward():
+    """Full Loco.forward (pre + model + post) on the reference's pifpaf fixture (mono) and on the
+    stereo fixture's left/right keypoints (stereo, all-vs-all + filter)."""
+    ann = json.load(open(os.path.join(REF, 'tests', '002282.png.pifpaf.json')))
+    boxes, keypoints = preprocess_pifpaf(ann, im_size=(1238, 374))
+    kk = synthetic.KITTI_K
+    model, sd = build('loco', 34, 9, 1024, 3, 1)
+    net = Loco(model=model, mode='mono', device=torch.device('cpu'))
+    dic = net.forward(keypoints, kk)
+    save = dict(keypoints=np.asarray(keypoints, dtype=np.float32), boxes=np.asarray(boxes, dtype=np.float32),
+                K=np.asarray(kk, dtype=np.float32), checksum=sd_checksum(sd))
+    save.update(dic_to_np(dic, 'out_'))
+    # post_process pieces used by Loco.post_process (net.py:192-215)
+    uv_centers = get_keypoints(keypoints, mode='center')
+    xy_centers = pixel_to_camera(uv_centers, kk, 1)
+    xyz = xyz_from_distance(dic['d'], xy_centers)
+    save['xy_centers'] = xy_centers.numpy()
+    save['xyz_from_distance'] = xyz.numpy()
+    np.savez_compressed(os.path.join(OUT, 'ref_loco_mono_pifpaf.npz'), **save)
+    print('loco mono', {k: v.shape for k, v in save.items() if hasattr(v, 'shape')})
+
+    kat = np.load(os.path.join(OUT, 'kat_stereo_val.npz'))
+    left = kat['kps'][:12, :, :17]
+    right = kat['kps'][:9, :, 17:]
+    model, sd = build('loco', 68, 10, 1024, 3, 2)
+    net = Loco(model=model, mode='stereo', device=torch.device('cpu'))
+    dic = net.forward(left.tolist(), kk, right.tolist())
+    save = dict(left=left, right=right, K=np.asarray(kk, dtype=np.float32), checksum=sd_checksum(sd))
+    save.update(dic_to_np(dic, 'out_'))
+    inputs, _ = preprocess_monstereo(torch.from_numpy(left), torch.from_numpy(right), torch.tensor(kk))
+    with torch.no_grad():
+        raw = model(inputs)
+    clustered = cluster_outputs(raw, right.shape[0])
+    fin, mask = filter_outputs(clustered)
+    save['pairs_x'] = inputs.numpy()
+    save['pairs_raw'] = raw.numpy()
+    save['filter_mask'] = mask.numpy()
+    save['filter_out'] = fin.numpy()
+    # no right poses: net.py:115-116
+    dic1 = net.forward(left.tolist(), kk, None)
+    save.update(dic_to_np(dic1, 'noright_'))
+    np.savez_compressed(os.path.join(OUT, 'ref_loco_stereo.npz'), **save)
+    print('loco stereo', save['out_xyzd'].shape, save['filter_mask'].sum())
+
+
+def ref_losses():
+    """MultiTaskLoss / AutoTuneMultiTaskLoss values and the full train-step gradients
+    (train-mode BN batch statistics, dropout p=0 so no RNG is involved)."""
+    for mode, isz, osz, seed in (('mono', 34, 9, 21), ('stereo', 68, 10, 22)):
+        tasks = ('d', 'x', 'y', 'h', 'w', 'l', 'ori') + (('aux',) if mode == 'stereo' else ())
+        lambdas = (1,) * len(tasks)
+        L, st, B = 64, 2, 48
+        sd = synthetic.make_state_dict('loco', isz, osz, L, st, seed)
+        model = LocoModel(isz, osz, L, 0.0, st, device='cpu')
+        model.load_state_dict(sd_to_torch(sd))
+        model.train()
+        x = synthetic.make_inputs(B, isz, seed=200 + seed)
+        y = synthetic.make_labels(B, stereo=(mode == 'stereo'), seed=300 + seed)
+        for auto in (False, True):
+            losses_tr, losses_val = CompositeLoss(tasks)()
+            if auto:
+                mt = AutoTuneMultiTaskLoss(losses_tr, losses_val, lambdas, tasks)
+                with torch.no_grad():
+                    mt.log_sigmas.copy_(torch.linspace(-0.3, 0.4, len(tasks)))
+            else:
+                mt = MultiTaskLoss(losses_tr, losses_val, lambdas, tasks)
+            model.load_state_dict(sd_to_torch(sd))
+            model.zero_grad()
+            out = model(torch.from_numpy(x))
+            out.retain_grad()
+            loss, vals = mt(out, torch.from_numpy(y), phase='train')
+            loss.backward()
+            save = dict(x=x, y=y, out=out.detach().numpy(), loss=float(loss), vals=np.array([float(v) for v in vals]),
+                        dout=out.grad.numpy(), cfg=np.array([isz, osz, L, st, seed, B]), checksum=sd_checksum(sd))
+            for k, p in model.named_parameters():
+                save['grad.' + k] = p.grad.numpy()
+            for k, b in model.named_buffers():
+                save['buf.' + k] = b.detach().numpy()  # running stats after one train-mode forward
+            if auto:
+                save['grad.log_sigmas'] = mt.log_sigmas.grad.numpy()
+                save['log_sigmas'] = mt.log_sigmas.detach().numpy()
+            with torch.no_grad():
+                _, vals_val = mt(out.detach(), torch.from_numpy(y), phase='val')
+            save['vals_val'] = np.array([float(v) for v in vals_val])
+            np.savez_compressed(os.path.join(OUT, 'ref_train_%s_%s.npz' % (mode, 'auto' if auto else 'mtl')), **save)
+            print('train', mode, auto, float(loss))
+
+
+def ref_epistemic():
+    """laplace_sampling (process.py:101-122) population check + unnormalize_bi."""
+    mu = torch.tensor([[10.0, 0.5], [25.0, 2.0], [40.0, 4.0]])
+    xx = laplace_sampling(mu, 100)
+    np.savez_compressed(os.path.join(OUT, 'ref_laplace_sampling.npz'), mu_bi=mu.numpy(), samples=xx.numpy(),
+                        bi=unnormalize_bi(torch.tensor([[10.0, -1.0], [25.0, 0.2]])).numpy())
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    kat_preprocess()
+    ref_forward()
+    ref_loco_forward()
+    ref_losses()
+    ref_epistemic()
+    print('done')
