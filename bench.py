@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""
+bench.py -- monoloco hot path on B200:  detections/s of the fused forward (pre-process -> LocoModel -> decode).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Contract (see the task statement / DESIGN.md §6):
+  * one step = one pass of the hot path over one batch of synthetic 17-keypoint detections
+    (BASELINE.json configs[1]: LocoModel mono 34->9, 3 stages x 1024, batch 4096 per GPU, fp32);
+  * `value`  = whole-job detections/s with inputs resident in HBM, timed with CUDA events on the launching stream,
+               L2 flushed (256 MiB memset) before every timed step, max over ranks;
+  * `e2e`    = same metric through the C-ABI host-buffer call (pinned host memory; H2D + kernel + D2H per step);
+  * `roofline`, `cpu_baseline`, `clocks`, `gpu_launches` as specified.
+  * --impl reference: the reference's CPU implementation of the path (oracle/torch_port.py = the same torch-eager
+    op sequence as the reference nn.Module) timed on the host cores.
+Multi-GPU: launched by torch.distributed.run; detections shard over ranks (weak scaling, 4096 per GPU), one
+all-gather of the [B,17] outputs per step (NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "detections/sec LocoModel(34->9, 3x1024) fused forward @ batch 4096 per GPU"
+UNIT = "detections/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get('hbm_gbs', 6650.0), 'measured', d
+    return 6650.0, 'fallback', {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(sd, x_np, budget_s=12.0, min_reps=3):
+    """detections/s of the reference's CPU path (torch eager, all host threads) on a bounded sample."""
+    from oracle import torch_port as T  # the one place bench.py executes oracle/: the timed CPU baseline
+    tsd = T.to_torch(sd)
+    x = torch.from_numpy(x_np)
+    with torch.no_grad():
+        for _ in range(2):
+            T.model_forward(tsd, x)
+        times = []
+        t_all = time.perf_counter()
+        while len(times) < min_reps or (time.perf_counter() - t_all < budget_s and len(times) < 200):
+            t0 = time.perf_counter()
+            T.model_forward(tsd, x)
+            times.append(time.perf_counter() - t0)
+    med = float(np.median(times))
+    return x_np.shape[0] / med, len(times), med
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores."""
+    if rank != 0:
+        return
+    from monoloco_b200 import synthetic
+    from oracle import loco_oracle as O
+    from oracle import torch_port as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+    B = args.batch
+    kps = synthetic.make_keypoints(B, seed=0)
+    tsd = T.to_torch(sd)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            x = O.preprocess_monoloco(kps, synthetic.KITTI_K)           # process.py:47-67
+            out = T.model_forward(tsd, torch.from_numpy(x))            # architectures.py:48-71
+            O.extract_outputs(out.numpy())                             # process.py:231-278
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = B / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LocoModel mono 34->9 L=1024 x3 stages, pre-process + forward + decode, batch %d, CPU" % B,
+                       "batch_per_step": B},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "%d steps x %d detections, torch-eager CPU restatement (oracle/torch_port.py)"
+                                       % (args.steps, B)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--batch', type=int, default=4096, help='detections per GPU per step')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--rows-per-group', type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from monoloco_b200 import synthetic, engine, packing, _lib as L_
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch
+    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+    eng = engine.LocoEngine(sd, device=dev)
+    lib = L_.lib()
+    kk = synthetic.KITTI_K
+    kps_host = torch.from_numpy(synthetic.make_keypoints(B, seed=rank)).pin_memory()
+    kps = kps_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gathered = torch.empty((world * B, 17), dtype=torch.float32, device=dev) if world > 1 else None
+    st = torch.cuda.current_stream(dev)
+
+    def step():
+        out = eng.forward(kps, kk=kk, kind=L_.IN_KPS, rows_per_group=args.rows_per_group)
+        if world > 1:
+            local = torch.cat((out['raw'], out['dec']), dim=1)
+            dist.all_gather_into_tensor(gathered, local)
+        return out
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- timed region: K steps, device-timed, L2 flushed before each
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.mlb_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        for e0, e1 in ev:
+            flush.zero_()
+            e0.record(st)
+            step()
+            e1.record(st)
+        torch.cuda.synchronize(dev)
+    launches = lib.mlb_launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    total_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in ev))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------- e2e through the host-buffer C-ABI call (pinned host memory)
+    out_host = {'raw': torch.empty((B, 9)).pin_memory(), 'dec': torch.empty((B, 8)).pin_memory()}
+    for _ in range(3):
+        eng.forward_host(kps_host, kk=kk, kind=L_.IN_KPS, out=out_host)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.forward_host(kps_host, kk=kk, kind=L_.IN_KPS, out=out_host)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        hbm_peak, peak_src, pk = peaks()
+        w_bytes = eng.packed.blob.size * 4
+        io_bytes = 204 + 36 + 32          # raw kps in + raw out + decoded out
+        alg_bytes = w_bytes + B * io_bytes
+        flops = packing.flops_per_detection(sd) * B
+        # single-GPU kernel time: at world == 1 the step is exactly one launch of loco_forward_kernel
+        achieved_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        ffma_peak = engine.probe_ffma_tflops(local_rank)
+        achieved_tf = flops / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "LocoModel mono 34->9 L=1024 x3 stages: raw keypoints [B,3,17] -> fused pre-process + "
+                                   "forward + decode, batch %d per GPU" % B,
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
+                       "l2": "flushed before every timed step (256 MiB memset)",
+                       "collective": "all_gather_into_tensor [B,17] fp32 per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 51 * 4, "d2h_bytes_per_step": B * 17 * 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes,
+                         "note": "at batch 4096 the path is FP32-FFMA bound (SURVEY.md §0.4); see fp32",
+                         "fp32": {"achieved": achieved_tf, "peak": ffma_peak, "unit": "TFLOP/s",
+                                  "frac": achieved_tf / ffma_peak if ffma_peak else None,
+                                  "peak_source": "measured in-run by mlb_probe_ffma (pure FFMA kernel)",
+                                  "algorithmic_flops": flops}},
+        }
+        if not args.no_cpu_baseline:
+            x = np.ascontiguousarray(synthetic.make_inputs(B, 34, seed=0))
+            torch.set_num_threads(os.cpu_count() or 1)
+            rate, reps, med = cpu_reference_rate(sd, x)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d x batch-%d model forwards (oracle/torch_port.py), median %.1f ms"
+                                              % (reps, B, med * 1e3)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

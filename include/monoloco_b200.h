@@ -1,0 +1,136 @@
+/*
+ * monoloco_b200 -- C ABI of the B200-native monoloco hot path (libmonoloco_b200.so).
+ *
+ * The reference (vita-epfl/monoloco @ f5e82c4) has no FFI on this path: its boundary is the Python API
+ * monoloco/network/net.py:30-133 (Loco.__init__/forward), architectures.py:48-71,135-145 (nn.Module.forward)
+ * and train/losses.py:59-73 (MultiTaskLoss.forward).  The entry points below are what a ctypes binding under
+ * that Python API binds (INTEGRATION.md shows the stub); every function cites the reference code it replaces.
+ *
+ * Conventions: plain C, no exceptions, int return codes (0 = ok, <0 = error, text via mlb_last_error()),
+ * caller-owned buffers, explicit cudaStream_t passed as void*.  All tensors are fp32 row-major.
+ * Thread-safety: one handle may be used from one thread at a time; distinct handles are independent.
+ */
+#ifndef MONOLOCO_B200_H_
+#define MONOLOCO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLB_ABI_VERSION 1
+#define MLB_MAX_OPS 32
+
+/* ---- layer program: one entry per Linear(+BN+ReLU+Dropout)(+residual) of architectures.py ---- */
+enum { MLB_OP_GEMM = 0, /* L-wide Linear, weights streamed through the TMA ring                    */
+       MLB_OP_HEAD = 1  /* narrow head Linear (w_fin / w_aux / MonolocoModel.w2), N <= 16          */ };
+
+enum { MLB_F_RELU     = 1,  /* nn.ReLU after the affine                                            */
+       MLB_F_SAVE_RES = 2,  /* output is the `x` of the next MyLinearSimple (architectures.py:88)  */
+       MLB_F_ADD_RES  = 4,  /* out = x + y                                   (architectures.py:100) */
+       MLB_F_DROPOUT  = 8,  /* top-level self.dropout site (architectures.py:53,66; net.py:141)    */
+       MLB_F_IN_XIN   = 16  /* reads the network input (first layer w1, architectures.py:50)       */ };
+
+typedef struct mlb_op {
+    int32_t type;      /* MLB_OP_*                                                                  */
+    int32_t K;         /* in_features                                                               */
+    int32_t Kpad;      /* K rounded up to the weight-chunk depth (zero padded)                      */
+    int32_t N;         /* out_features                                                              */
+    int32_t flags;     /* MLB_F_*                                                                   */
+    int32_t out_col;   /* HEAD: first column of the raw [B,out] output it writes                    */
+    int64_t w_off;     /* float offset into the packed blob: GEMM = chunked W^T, HEAD = W [N][K]    */
+    int64_t scale_off; /* GEMM: per-feature scale [N]  (folded BatchNorm1d eval, eps 1e-5)          */
+    int64_t shift_off; /* GEMM: per-feature shift [N]; HEAD: bias [N]                               */
+} mlb_op;
+
+enum { MLB_DECODE_NONE = 0,
+       MLB_DECODE_LOCO = 1,  /* process.py:231-278 extract_outputs (monoloco_pp / monstereo)        */
+       MLB_DECODE_MONO = 2,  /* process.py:330-360 extract_outputs_mono (legacy monoloco_p)         */
+       MLB_DECODE_DB   = 3   /* net.py:95-100 legacy monoloco: d = o0, bi = exp(o1)*o0              */ };
+
+typedef struct mlb_model_desc {
+    int32_t abi_version;  /* MLB_ABI_VERSION                                                        */
+    int32_t input_size;   /* 34 mono | 68 stereo                     (net.py:45-58)                 */
+    int32_t output_size;  /* raw output columns: 2 | 9 | 10                                         */
+    int32_t linear_size;  /* hidden width L: multiple of 64, <= 1024  (net.py:30, hyp_tuning.py:52) */
+    int32_t n_ops;
+    int32_t decode_kind;  /* MLB_DECODE_*                                                           */
+    float   p_dropout;    /* nn.Dropout p (architectures.py:46)                                     */
+    int32_t reserved;
+} mlb_model_desc;
+
+typedef struct mlb_model* mlb_handle;
+
+/* Build a device-resident model from a host blob packed by monoloco_b200/packing.py (replaces
+ * Loco.__init__'s load_state_dict + .to(device), net.py:68-81).  `device` is the CUDA ordinal. */
+int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const float* packed_host, size_t n_floats,
+               int device, mlb_handle* out);
+/* Re-upload the packed blob (same layout) -- e.g. after an optimizer step. */
+int mlb_update_weights(mlb_handle h, const float* packed_host, size_t n_floats, void* stream);
+void mlb_destroy(mlb_handle h);
+const char* mlb_last_error(void);
+int mlb_abi_version(void);
+/* number of SMs / resident CTAs the forward uses on this handle's device */
+int mlb_num_sms(mlb_handle h);
+
+/* ---- inference ---- */
+enum { MLB_IN_X = 0,          /* pre-processed network input [B, input_size] (nn.Module.forward)    */
+       MLB_IN_KPS = 1,        /* raw keypoints [B,3,17] (u,v,conf rows): process.py:47-67 fused      */
+       MLB_IN_KPS_STEREO = 2  /* left [L,3,17] + right [R,3,17], all-vs-all rows l*R+r: :25-44 fused */ };
+
+enum { MLB_FWD_ZERO_CENTER = 1, /* preprocess_monoloco(zero_center=True) (net.py:96, legacy)        */
+       MLB_FWD_DROPOUT     = 2, /* MC-dropout pass: top-level dropout sites active (net.py:141)     */
+       MLB_FWD_RES_TMEM    = 4  /* stash the residual in Tensor Memory instead of the L2 scratch    */ };
+
+typedef struct mlb_forward_args {
+    int32_t input_kind;     /* MLB_IN_*                                                             */
+    int32_t flags;          /* MLB_FWD_*                                                            */
+    int32_t n_rows;         /* B; for MLB_IN_KPS_STEREO must equal n_left * n_right                 */
+    int32_t n_left;         /* stereo only                                                          */
+    int32_t n_right;        /* stereo only                                                          */
+    int32_t rows_per_group; /* 0 = auto; else 4..8 (tile = 4*rows_per_group detections per CTA)     */
+    float kinv[9];          /* K^-1 row-major (camera.py:25), only for MLB_IN_KPS*                  */
+    float z_met;            /* camera.py:27 scale; 0 -> 10 (process.py:59-60)                       */
+    const float* x;         /* input (see input_kind); left keypoints for stereo                    */
+    const float* x_right;   /* right keypoints [R,3,17] (stereo)                                    */
+    float* out_raw;         /* [B, output_size]            required                                 */
+    float* out_dec;         /* [B, 8] = x,y,z,d,bi,yaw_pred,yaw_orig,sigmoid(aux)   or NULL         */
+    float* out_xyzc;        /* [B, 4] = xyz_from_distance(d, K^-1[u_c,v_c,1]) (camera.py:161-177,
+                               net.py:192-213) and its norm; MLB_IN_KPS only, or NULL               */
+    float* out_x;           /* [B, input_size] the pre-processed network input, or NULL             */
+    const uint8_t* drop_mask; /* [sites][B][L] keep-mask (1 keep) for MLB_FWD_DROPOUT, or NULL      */
+    uint64_t drop_seed;     /* in-kernel counter RNG seed when drop_mask == NULL                    */
+} mlb_forward_args;
+
+/* Fused pre-process -> MLP -> heads -> decode on DEVICE buffers (replaces net.py:92-124 body:
+ * preprocess_*, self.model(inputs), extract_outputs). Asynchronous on `stream`. */
+int mlb_forward(mlb_handle h, const mlb_forward_args* args, void* stream);
+/* Same with HOST buffers: H2D of the inputs, kernel, D2H of every non-NULL output, then stream sync
+ * (replaces net.py:92-93 `.to(device)` + process.py:261-263 `.detach().cpu()`). */
+int mlb_forward_host(mlb_handle h, const mlb_forward_args* host_args, void* stream);
+
+/* pre-process only: [B,3,17] -> [B,34] (process.py:47-67), for callers such as
+ * prep/preprocess_kitti.py:193 that never run the network.  Device buffers. */
+int mlb_preprocess(const float* kps, int n_rows, const float kinv[9], float z_met, int zero_center,
+                   float* out_x, void* stream);
+
+/* monstereo arg-max filter (process.py:307-327): rows [n_left*n_right, out] viewed [n_left, n_right, out];
+ * keeps, per left pose, every row whose last column >= the max over its right poses (ties kept, row-major
+ * order).  Gathers raw (and dec/xyzc if non-NULL) rows into sel_*; writes the kept-row count to *n_sel_dev
+ * and the kept flat row indices to sel_idx (capacity n_left*n_right).  Device buffers. */
+int mlb_stereo_filter(const float* raw, const float* dec, int n_left, int n_right, int out_size,
+                      float* sel_raw, float* sel_dec, int32_t* sel_idx, int32_t* n_sel_dev, void* stream);
+
+/* FP32-FFMA throughput probe (roofline denominator for the fp32-bound regime): every thread of
+ * `blocks` x 512 threads runs `iters` x 16 independent FFMAs.  Returns flops launched via *flops. */
+int mlb_probe_ffma(int device, int blocks, int iters, double* flops, void* stream);
+
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t mlb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOLOCO_B200_H_ */

@@ -1,0 +1,73 @@
+"""ctypes binding of include/monoloco_b200.h.  There is NO fallback: if the CUDA library is missing
+or cannot be loaded every product entry point raises (the product path never runs on the CPU)."""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+MLB_ABI_VERSION = 1
+MLB_MAX_OPS = 32
+OP_GEMM, OP_HEAD = 0, 1
+F_RELU, F_SAVE_RES, F_ADD_RES, F_DROPOUT, F_IN_XIN = 1, 2, 4, 8, 16
+DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
+IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
+FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM = 1, 2, 4
+
+EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
+           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_probe_ffma',
+           'mlb_launch_count']
+
+
+class MlbOp(C.Structure):
+    _fields_ = [('type', C.c_int32), ('K', C.c_int32), ('Kpad', C.c_int32), ('N', C.c_int32), ('flags', C.c_int32),
+                ('out_col', C.c_int32), ('w_off', C.c_int64), ('scale_off', C.c_int64), ('shift_off', C.c_int64)]
+
+
+class MlbModelDesc(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('input_size', C.c_int32), ('output_size', C.c_int32),
+                ('linear_size', C.c_int32), ('n_ops', C.c_int32), ('decode_kind', C.c_int32),
+                ('p_dropout', C.c_float), ('reserved', C.c_int32)]
+
+
+class MlbForwardArgs(C.Structure):
+    _fields_ = [('input_kind', C.c_int32), ('flags', C.c_int32), ('n_rows', C.c_int32), ('n_left', C.c_int32),
+                ('n_right', C.c_int32), ('rows_per_group', C.c_int32), ('kinv', C.c_float * 9), ('z_met', C.c_float),
+                ('x', C.c_void_p), ('x_right', C.c_void_p), ('out_raw', C.c_void_p), ('out_dec', C.c_void_p),
+                ('out_xyzc', C.c_void_p), ('out_x', C.c_void_p), ('drop_mask', C.c_void_p), ('drop_seed', C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "monoloco_b200: %s is missing -- build it with `python -m monoloco_b200.build` "
+            "(there is no CPU fallback for the product path)" % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    l.mlb_last_error.restype = C.c_char_p
+    l.mlb_create.argtypes = [C.POINTER(MlbModelDesc), C.POINTER(MlbOp), C.c_void_p, C.c_size_t, C.c_int,
+                             C.POINTER(C.c_void_p)]
+    l.mlb_update_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    l.mlb_destroy.argtypes = [C.c_void_p]
+    l.mlb_destroy.restype = None
+    l.mlb_num_sms.argtypes = [C.c_void_p]
+    l.mlb_forward.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
+    l.mlb_forward_host.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
+    l.mlb_preprocess.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    l.mlb_stereo_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mlb_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    l.mlb_launch_count.restype = C.c_uint64
+    if l.mlb_abi_version() != MLB_ABI_VERSION:
+        raise RuntimeError("monoloco_b200: ABI version mismatch between _lib.py and the shared library")
+    _lib = l
+    return l
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s" % (what, lib().mlb_last_error().decode()))

@@ -1,0 +1,208 @@
+"""Thin Python owner of an `mlb_handle` (include/monoloco_b200.h).
+
+PyTorch is used for device memory and streams only; every computation on the hot path is a kernel in
+libmonoloco_b200.so.  There is no CPU fallback: constructing an engine without the library / a B200 raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L_
+from .packing import pack_state_dict
+
+DEC_COLS = ('x', 'y', 'z', 'd', 'bi', 'yaw_pred', 'yaw_orig', 'aux')
+
+
+def kinv_from_kk(kk):
+    """K^-1 (utils/camera.py:25) computed once on the host in float64, rounded to fp32."""
+    k = np.asarray(kk.detach().cpu().numpy() if hasattr(kk, 'detach') else kk, dtype=np.float64).reshape(3, 3)
+    return np.linalg.inv(k).astype(np.float32).reshape(9)
+
+
+class LocoEngine:
+    def __init__(self, state_dict, p_dropout=0.2, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("monoloco_b200: no CUDA device -- the hot path has no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("monoloco_b200: device must be a CUDA device")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._lib = L_.lib()
+        self._h = C.c_void_p()
+        self.p_dropout = p_dropout
+        self._create(state_dict)
+
+    # ---------------------------------------------------------------- lifetime
+    def _create(self, state_dict):
+        pm = pack_state_dict(state_dict, self.p_dropout)
+        self.packed = pm
+        d = pm.desc
+        desc = L_.MlbModelDesc(L_.MLB_ABI_VERSION, d['input_size'], d['output_size'], d['linear_size'], d['n_ops'],
+                               d['decode_kind'], d['p_dropout'], 0)
+        ops = (L_.MlbOp * len(pm.ops))()
+        for i, o in enumerate(pm.ops):
+            ops[i] = L_.MlbOp(o['type'], o['K'], o['Kpad'], o['N'], o['flags'], o['out_col'], o['w_off'],
+                              o['scale_off'], o['shift_off'])
+        self._blob = pm.blob  # keep alive during the call
+        L_.check(self._lib.mlb_create(C.byref(desc), ops, pm.blob.ctypes.data_as(C.c_void_p), pm.blob.size,
+                                      self.index, C.byref(self._h)), 'mlb_create')
+        self.input_size, self.output_size, self.linear_size = d['input_size'], d['output_size'], d['linear_size']
+        self.decode_kind = d['decode_kind']
+        self.n_sms = self._lib.mlb_num_sms(self._h)
+
+    def update_weights(self, state_dict):
+        """Re-pack and upload (same architecture), e.g. after an optimizer step / load_state_dict."""
+        pm = pack_state_dict(state_dict, self.p_dropout)
+        if pm.blob.size != self.packed.blob.size or pm.desc != self.packed.desc:
+            self.close()
+            self._create(state_dict)
+            return
+        self.packed = pm
+        L_.check(self._lib.mlb_update_weights(self._h, pm.blob.ctypes.data_as(C.c_void_p), pm.blob.size,
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                 'mlb_update_weights')
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self._lib.mlb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    # ---------------------------------------------------------------- forward on device tensors
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self, x, x_right=None, kk=None, kind=L_.IN_X, want_dec=True, want_xyzc=False, want_x=False,
+                zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=False):
+        """x: float32 CUDA tensor ([B,in] | [B,3,17] | left [L,3,17]).  Returns dict of CUDA tensors."""
+        assert x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        a = L_.MlbForwardArgs()
+        a.input_kind = kind
+        a.flags = (L_.FWD_ZERO_CENTER if zero_center else 0) | (L_.FWD_DROPOUT if dropout else 0) | \
+                  (L_.FWD_RES_TMEM if res_tmem else 0)
+        if kind == L_.IN_KPS_STEREO:
+            x_right = x_right.contiguous()
+            n_left, n_right = x.shape[0], x_right.shape[0]
+            B = n_left * n_right
+            a.n_left, a.n_right = n_left, n_right
+            a.x_right = x_right.data_ptr()
+        else:
+            B = x.shape[0]
+        if kind != L_.IN_X:
+            kinv = kinv_from_kk(kk)
+            for i in range(9):
+                a.kinv[i] = float(kinv[i])
+            a.z_met = 10.0
+        a.n_rows = B
+        a.rows_per_group = rows_per_group
+        out = {'raw': torch.empty((B, self.output_size), dtype=torch.float32, device=self.device)}
+        a.x = x.data_ptr()
+        a.out_raw = out['raw'].data_ptr()
+        if want_dec:
+            out['dec'] = torch.empty((B, 8), dtype=torch.float32, device=self.device)
+            a.out_dec = out['dec'].data_ptr()
+        if want_xyzc:
+            out['xyzc'] = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+            a.out_xyzc = out['xyzc'].data_ptr()
+        if want_x:
+            out['x'] = torch.empty((B, self.input_size), dtype=torch.float32, device=self.device)
+            a.out_x = out['x'].data_ptr()
+        if drop_mask is not None:
+            assert drop_mask.is_cuda and drop_mask.dtype == torch.uint8
+            drop_mask = drop_mask.contiguous()
+            a.drop_mask = drop_mask.data_ptr()
+        a.drop_seed = int(drop_seed)
+        if B > 0:
+            L_.check(self._lib.mlb_forward(self._h, C.byref(a), self._stream()), 'mlb_forward')
+        return out
+
+    def forward_host(self, x, x_right=None, kk=None, kind=L_.IN_X, want_dec=True, want_xyzc=False, out=None,
+                     rows_per_group=0):
+        """Host (numpy / pinned torch CPU) buffers in, host buffers out; H2D + kernel + D2H + sync inside."""
+        xt = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        a = L_.MlbForwardArgs()
+        a.input_kind = kind
+        if kind == L_.IN_KPS_STEREO:
+            xr = x_right if isinstance(x_right, torch.Tensor) else torch.from_numpy(
+                np.ascontiguousarray(x_right, dtype=np.float32))
+            a.n_left, a.n_right = xt.shape[0], xr.shape[0]
+            B = a.n_left * a.n_right
+            a.x_right = xr.data_ptr()
+        else:
+            B = xt.shape[0]
+        if kind != L_.IN_X:
+            kinv = kinv_from_kk(kk)
+            for i in range(9):
+                a.kinv[i] = float(kinv[i])
+            a.z_met = 10.0
+        a.n_rows = B
+        a.rows_per_group = rows_per_group
+        if out is None:
+            out = {'raw': torch.empty((B, self.output_size), dtype=torch.float32)}
+            if want_dec:
+                out['dec'] = torch.empty((B, 8), dtype=torch.float32)
+            if want_xyzc:
+                out['xyzc'] = torch.empty((B, 4), dtype=torch.float32)
+        a.x = xt.data_ptr()
+        a.out_raw = out['raw'].data_ptr()
+        if 'dec' in out:
+            a.out_dec = out['dec'].data_ptr()
+        if 'xyzc' in out:
+            a.out_xyzc = out['xyzc'].data_ptr()
+        if B > 0:
+            L_.check(self._lib.mlb_forward_host(self._h, C.byref(a), self._stream()), 'mlb_forward_host')
+        return out
+
+    def stereo_filter(self, raw, dec, n_left, n_right):
+        """process.py:307-327 on device; returns (sel_raw, sel_dec, sel_idx) trimmed to the kept rows."""
+        B = n_left * n_right
+        sel_raw = torch.empty_like(raw)
+        sel_dec = torch.empty_like(dec) if dec is not None else None
+        sel_idx = torch.empty((B,), dtype=torch.int32, device=self.device)
+        n_sel = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        L_.check(self._lib.mlb_stereo_filter(raw.data_ptr(), dec.data_ptr() if dec is not None else None, n_left,
+                                             n_right, raw.shape[1], sel_raw.data_ptr(),
+                                             sel_dec.data_ptr() if dec is not None else None, sel_idx.data_ptr(),
+                                             n_sel.data_ptr(), self._stream()), 'mlb_stereo_filter')
+        n = int(n_sel.item())
+        return sel_raw[:n], (sel_dec[:n] if dec is not None else None), sel_idx[:n]
+
+
+def preprocess_device(kps, kk, zero_center=False):
+    """process.py:47-67 as a stand-alone kernel: [B,3,17] CUDA tensor -> [B,34] CUDA tensor."""
+    lib = L_.lib()
+    assert kps.is_cuda and kps.dtype == torch.float32
+    kps = kps.contiguous()
+    B = kps.shape[0]
+    out = torch.empty((B, 34), dtype=torch.float32, device=kps.device)
+    kinv = (C.c_float * 9)(*[float(v) for v in kinv_from_kk(kk)])
+    if B:
+        L_.check(lib.mlb_preprocess(kps.data_ptr(), B, kinv, 10.0, int(zero_center), out.data_ptr(),
+                                    C.c_void_p(torch.cuda.current_stream(kps.device).cuda_stream)), 'mlb_preprocess')
+    return out
+
+
+def probe_ffma_tflops(device_index=0, iters=4096, reps=5):
+    """Measured FP32-FFMA throughput of this GPU (roofline denominator in the fp32-bound regime)."""
+    lib = L_.lib()
+    n_sm = torch.cuda.get_device_properties(device_index).multi_processor_count
+    blocks = n_sm * 4
+    flops = C.c_double()
+    st = torch.cuda.current_stream()
+    best = 0.0
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        L_.check(lib.mlb_probe_ffma(device_index, blocks, iters, C.byref(flops), C.c_void_p(st.cuda_stream)), 'probe')
+        e1.record(st)
+        e1.synchronize()
+        best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -118,3 +118,30 @@ def test_laplace_population_std():
     pop = O.laplace_std(f['mu_bi'][:, 1])
     assert np.allclose(est, pop, rtol=0.35)  # 100 samples: statistical agreement only
     assert np.allclose(O.unnormalize_bi(np.array([[10.0, -1.0], [25.0, 0.2]], dtype=np.float32)), f['bi'], rtol=1e-6)
+
+
+@pytest.mark.parametrize('mode', ['mono', 'stereo'])
+@pytest.mark.parametrize('auto', [False, True])
+def test_torch_port_train_step(mode, auto):
+    """oracle/torch_port.py (autograd) vs the live reference: loss, per-task values, d(out), every parameter grad,
+    BN running-stat update."""
+    import torch
+    from oracle import torch_port as T
+    f = np.load(os.path.join(GOLDEN, 'ref_train_%s_%s.npz' % (mode, 'auto' if auto else 'mtl')))
+    isz, osz, L, st, seed, B = [int(v) for v in f['cfg']]
+    tasks = ('d', 'x', 'y', 'h', 'w', 'l', 'ori') + (('aux',) if mode == 'stereo' else ())
+    sd = T.to_torch(synthetic.make_state_dict('loco', isz, osz, L, st, seed), requires_grad=True)
+    ls = torch.tensor(f['log_sigmas'], requires_grad=True) if auto else None
+    out = T.model_forward(sd, torch.from_numpy(f['x']), training=True, p_dropout=0.0)
+    loss, vals = T.multi_task_loss(out, torch.from_numpy(f['y']), tasks, log_sigmas=ls)
+    loss.backward()
+    assert abs(float(loss) - float(f['loss'])) <= 2e-6 * abs(float(f['loss']))
+    assert np.allclose(out.detach().numpy(), f['out'], rtol=1e-5, atol=1e-5)
+    for k in f.files:
+        if k.startswith('grad.') and k != 'grad.log_sigmas':
+            g = sd[k[5:]].grad.numpy()
+            assert np.allclose(g, f[k], rtol=1e-4, atol=1e-6 * max(1.0, float(np.abs(f[k]).max()))), k
+        if k.startswith('buf.') and 'num_batches' not in k:
+            assert np.allclose(sd[k[4:]].detach().numpy(), f[k], rtol=1e-5, atol=1e-6), k
+    if auto:
+        assert np.allclose(ls.grad.numpy(), f['grad.log_sigmas'], rtol=1e-5)
