@@ -54,7 +54,7 @@ typedef struct mlb_model_desc {
     int32_t abi_version;  /* MLB_ABI_VERSION                                                        */
     int32_t input_size;   /* 34 mono | 68 stereo                     (net.py:45-58)                 */
     int32_t output_size;  /* raw output columns: 2 | 9 | 10                                         */
-    int32_t linear_size;  /* hidden width L: multiple of 64, <= 1024  (net.py:30, hyp_tuning.py:52) */
+    int32_t linear_size;  /* hidden width L: multiple of 128, <= 1024 (net.py:30, hyp_tuning.py:52) */
     int32_t n_ops;
     int32_t decode_kind;  /* MLB_DECODE_*                                                           */
     float   p_dropout;    /* nn.Dropout p (architectures.py:46)                                     */
@@ -90,7 +90,7 @@ typedef struct mlb_forward_args {
     int32_t n_rows;         /* B; for MLB_IN_KPS_STEREO must equal n_left * n_right                 */
     int32_t n_left;         /* stereo only                                                          */
     int32_t n_right;        /* stereo only                                                          */
-    int32_t rows_per_group; /* 0 = auto; else 4..8 (tile = 4*rows_per_group detections per CTA)     */
+    int32_t rows_per_group; /* 0 = auto; else 8,10,..,16 (tile = 2*rows_per_group detections / CTA)  */
     float kinv[9];          /* K^-1 row-major (camera.py:25), only for MLB_IN_KPS*                  */
     float z_met;            /* camera.py:27 scale; 0 -> 10 (process.py:59-60)                       */
     const float* x;         /* input (see input_kind); left keypoints for stereo                    */
@@ -124,7 +124,8 @@ int mlb_stereo_filter(const float* raw, const float* dec, int n_left, int n_righ
                       float* sel_raw, float* sel_dec, int32_t* sel_idx, int32_t* n_sel_dev, void* stream);
 
 /* FP32-FFMA throughput probe (roofline denominator for the fp32-bound regime): every thread of
- * `blocks` x 512 threads runs `iters` x 16 independent FFMAs.  Returns flops launched via *flops. */
+ * `blocks` x 512 threads runs |iters| x 128 FMAs in 16 independent chains (iters < 0: packed fma.rn.f32x2).
+ * Returns flops launched via *flops. */
 int mlb_probe_ffma(int device, int blocks, int iters, double* flops, void* stream);
 
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */

@@ -7,12 +7,12 @@
 
 namespace mlb {
 
-constexpr int MP = 32;        // detection rows per CTA tile as laid out in shared memory (4 groups x 8)
+constexpr int MP = 32;        // detection rows per CTA tile as laid out in shared memory (2 groups x 16)
 constexpr int KC = 4;         // k-steps per weight chunk (one TMA bulk copy = KC * L floats)
 constexpr int NSTAGE = 4;     // weight-ring depth
 constexpr int KIN_MAX = 68;   // largest network input (monstereo)
 constexpr int OUT_LD = 16;    // raw-output staging row stride (output_size <= 16)
-constexpr int MAX_THREADS = 512;
+constexpr int MAX_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg 240 / 24)
 
 // error codes written to the device error flag
 enum { ERR_NONE = 0, ERR_MBAR_TIMEOUT = 1 };

@@ -15,8 +15,10 @@
 //   * weights are pre-packed per layer as chunks [KC][L] of W^T; one elected thread streams them L2 -> smem
 //     with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) through a NSTAGE ring guarded by
 //     full/empty mbarriers; the stream runs ahead across layer and tile boundaries;
-//   * 16 warps x (8 row-groups-of-lanes x 8 col-groups) register-tile the [4*TM, L] x [L, L] product:
-//     each thread holds TM x 8 fp32 accumulators, 2+2 LDS.128 per 8*TM FFMA;
+//   * 8 consumer warps (+1 producer warp) register-tile the [2*TM, L] x [L, L] product: a warp owns 128 output
+//     columns, lanes = 2 row groups x 16 column groups, each thread holds TM x 8 fp32 accumulators (TM <= 16);
+//     per k-step TM/4 broadcast LDS.128 (A) + 2 conflict-free LDS.128 (B) feed 8*TM FFMA -- the tall thread tile
+//     keeps the shared-memory pipe (128 B/clk/SM, the binding limit of an 8x8 tile) at ~55 % of the FFMA time;
 //   * the residual `x` of MyLinearSimple is stashed per thread in an L2-resident scratch (or Tensor Memory).
 #include <cuda_runtime.h>
 #include <math.h>
@@ -52,48 +54,45 @@ struct FwdParams {
     int* err_flag;
 };
 
-// weight-stream producer state (lives in thread 0's registers)
-struct Producer {
-    unsigned q_issue;
-    int tile, op, chunk;
-};
+// local row r of a tile -> shared-memory row (2 groups of 16 slots, TM used per group)
+__device__ __forceinline__ int smem_row(int r, int tm) { return (r / tm) * 16 + (r % tm); }
 
-__device__ __forceinline__ void produce_upto(Producer& pr, unsigned target, const FwdParams& p, float* ring, uint64_t* full,
-                                             uint64_t* empty, int L) {
-    while (pr.q_issue < target) {
-        // advance to the next GEMM chunk of this CTA's tile sequence
-        while (pr.tile < p.n_tiles) {
-            const mlb_op& op = p.ops[pr.op];
-            if (op.type == MLB_OP_GEMM && pr.chunk < op.Kpad / KC) break;
-            pr.op++;
-            pr.chunk = 0;
-            if (pr.op == p.n_ops) {
-                pr.op = 0;
-                pr.tile += gridDim.x;
-            }
-        }
-        if (pr.tile >= p.n_tiles) return;
-        const mlb_op& op = p.ops[pr.op];
-        const unsigned stage = pr.q_issue % NSTAGE;
-        if (pr.q_issue >= NSTAGE) mbar_wait(&empty[stage], ((pr.q_issue / NSTAGE) - 1) & 1, p.err_flag);
-        const uint32_t bytes = (uint32_t)(KC * L * sizeof(float));
-        mbar_expect_tx(&full[stage], bytes);
-        tma_bulk_g2s(ring + (size_t)stage * KC * L, p.blob + op.w_off + (size_t)pr.chunk * KC * L, bytes, &full[stage]);
-        pr.q_issue++;
-        pr.chunk++;
-    }
+__device__ __forceinline__ void consumer_sync(int n_consumer_threads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_consumer_threads) : "memory");
 }
 
-__device__ __forceinline__ int smem_row(int r, int tm) { return (r / tm) * 8 + (r % tm); }
+// The weight stream: every GEMM chunk of every tile this CTA owns, in consumption order.
+__device__ __forceinline__ void producer_loop(const FwdParams& p, float* ring, uint64_t* full, uint64_t* empty, int L) {
+    unsigned q = 0;
+    const uint32_t bytes = (uint32_t)(KC * L * sizeof(float));
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const mlb_op& op = p.ops[oi];
+            if (op.type != MLB_OP_GEMM) continue;
+            const float* src = p.blob + op.w_off;
+            const int nchunks = op.Kpad / KC;
+            for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                const unsigned stage = q % NSTAGE;
+                if (q >= NSTAGE) mbar_wait(&empty[stage], ((q / NSTAGE) - 1) & 1, p.err_flag);
+                mbar_expect_tx(&full[stage], bytes);
+                tma_bulk_g2s(ring + (size_t)stage * KC * L, src + (size_t)ch * KC * L, bytes, &full[stage]);
+            }
+        }
+    }
+}
 
 template <int TM>
 __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int L = p.L;  // == nwarps * 64
-    const int g = lane >> 3, c = lane & 7;
-    constexpr int ROWS = 4 * TM;
+    const int L = p.L;
+    const int nwarps = L >> 7;          // active consumer warps: one per 128 hidden columns
+    const int nthreads = nwarps << 5;   // active consumer threads
+    const int prod_warp = (int)(blockDim.x >> 5) - 4;  // first warp of the producer warpgroup
+    const int g = lane >> 4, c = lane & 15;
+    constexpr int ROWS = 2 * TM;
+    constexpr int A4 = (TM + 3) / 4;  // LDS.128 per k-step for the A fragment
+    constexpr int RES_STRIDE = 256;   // residual scratch: [cta][TM*8][256 consumer threads], thread-private
 
     float* act = reinterpret_cast<float*>(smem_raw);  // [L][MP]
     float* xin = act + (size_t)L * MP;                 // [KIN_MAX][MP]
@@ -105,9 +104,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + NSTAGE);
 
     const bool res_tmem = (p.flags & MLB_FWD_RES_TMEM) != 0;
-    const uint32_t tmem_cols = nwarps <= 4 ? 64u : (nwarps <= 8 ? 128u : 256u);
+    const uint32_t tmem_cols = nwarps <= 1 ? 128u : (nwarps <= 4 ? 128u : 256u);
 
-    for (int i = tid; i < L * MP + KIN_MAX * MP + MP * OUT_LD + MP * 4; i += nthreads) act[i] = 0.f;
+    for (int i = tid; i < L * MP + KIN_MAX * MP + MP * OUT_LD + MP * 4; i += blockDim.x) act[i] = 0.f;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
@@ -115,293 +114,298 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
         }
         mbar_fence_init();
     }
-    if (res_tmem && warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-    tmem_fence_before();
+    if (res_tmem) {
+        if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+        tmem_fence_before();
+    }
     __syncthreads();
-    tmem_fence_after();
-    uint32_t tmem_base = 0;
-    if (res_tmem) tmem_base = *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+    if (res_tmem) tmem_fence_after();
 
-    Producer pr;
-    pr.q_issue = 0;
-    pr.tile = blockIdx.x;
-    pr.op = 0;
-    pr.chunk = 0;
-    unsigned q = 0;  // chunks consumed so far (identical in every warp)
+    if (warp >= prod_warp) {
+        // ================================================================ producer warpgroup (1 elected thread works)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == prod_warp && lane == 0) producer_loop(p, ring, full, empty, L);
+    } else {
+        // ================================================================ consumer warpgroups
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+        if (warp < nwarps) {
+        uint32_t tmem_base = 0;
+        if (res_tmem) tmem_base = *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+        unsigned q = 0;  // chunks consumed so far (identical in every consumer warp)
+        const float zm = p.z_met;
+        const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
+        // this thread's 8 output columns: n0 + {0..3} and n0 + 64 + {0..3}
+        const int n0 = warp * 128 + c * 4;
 
-    const float zm = p.z_met;
-    const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int row0 = tile * ROWS;
+            const int rows_here = min(ROWS, p.n_rows - row0);
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int row0 = tile * ROWS;
-        const int rows_here = min(ROWS, p.n_rows - row0);
-
-        // -------------------------------------------------------------------- pre-process -> xin[k][row]
-        if (p.input_kind == MLB_IN_X) {
-            // nn.Module.forward input [B, in]; transpose into the k-major tile, zero-fill padding
-            for (int idx = tid; idx < ROWS * p.kpad0; idx += nthreads) {
-                const int r = idx / p.kpad0, k = idx % p.kpad0;
-                float v = 0.f;
-                if (r < rows_here && k < p.in_size) v = __ldg(p.x + (size_t)(row0 + r) * p.in_size + k);
-                xin[k * MP + smem_row(r, TM)] = v;
-            }
-        } else {
-            const bool stereo = p.input_kind == MLB_IN_KPS_STEREO;
-            // bbox centre of the 17 keypoints (camera.py:82-86), mono only: zero-centering + xyz_from_distance ray
-            if (!stereo && tid < ROWS) {
-                const int r = tid, sr = smem_row(r, TM);
-                float uc = 0.f, vc = 0.f;
-                if (r < rows_here) {
-                    const float* kp = p.x + (size_t)(row0 + r) * 51;
-                    float umin = __ldg(kp), umax = umin, vmin = __ldg(kp + 17), vmax = vmin;
-                    for (int j = 1; j < 17; ++j) {
+            // ---------------------------------------------------------------- pre-process -> xin[k][row]
+            if (p.input_kind == MLB_IN_X) {
+                // nn.Module.forward input [B, in]; transpose into the k-major tile, zero-fill padding
+                for (int idx = tid; idx < ROWS * p.kpad0; idx += nthreads) {
+                    const int r = idx / p.kpad0, k = idx % p.kpad0;
+                    float v = 0.f;
+                    if (r < rows_here && k < p.in_size) v = __ldg(p.x + (size_t)(row0 + r) * p.in_size + k);
+                    xin[k * MP + smem_row(r, TM)] = v;
+                }
+            } else {
+                const bool stereo = p.input_kind == MLB_IN_KPS_STEREO;
+                // bbox centre of the 17 keypoints (camera.py:82-86), mono only: zero-centering + xyz_from_distance ray
+                if (!stereo && tid < ROWS) {
+                    const int r = tid, sr = smem_row(r, TM);
+                    float uc = 0.f, vc = 0.f;
+                    if (r < rows_here) {
+                        const float* kp = p.x + (size_t)(row0 + r) * 51;
+                        float umin = __ldg(kp), umax = umin, vmin = __ldg(kp + 17), vmax = vmin;
+                        for (int j = 1; j < 17; ++j) {
+                            const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
+                            umin = fminf(umin, u), umax = fmaxf(umax, u);
+                            vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+                        }
+                        uc = __fadd_rn(__fdiv_rn(__fsub_rn(umax, umin), 2.f), umin);
+                        vc = __fadd_rn(__fdiv_rn(__fsub_rn(vmax, vmin), 2.f), vmin);
+                    }
+                    cen[sr * 4 + 0] = uc;
+                    cen[sr * 4 + 1] = vc;
+                    cen[sr * 4 + 2] = (uc * k0 + vc * k1 + k2) * zm;
+                    cen[sr * 4 + 3] = (uc * k3 + vc * k4 + k5) * zm;
+                }
+                if (p.flags & MLB_FWD_ZERO_CENTER) consumer_sync(nthreads);
+                for (int idx = tid; idx < ROWS * 17; idx += nthreads) {
+                    const int r = idx / 17, j = idx % 17, sr = smem_row(r, TM);
+                    float xl = 0.f, yl = 0.f, xd = 0.f, yd = 0.f;
+                    if (r < rows_here) {
+                        const int grow = row0 + r;
+                        const int li = stereo ? grow / p.n_right : grow;
+                        const float* kp = p.x + (size_t)li * 51;
                         const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
-                        umin = fminf(umin, u), umax = fmaxf(umax, u);
-                        vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+                        xl = (u * k0 + v * k1 + k2) * zm;  // camera.py:26-27, rows 0/1 of [u v 1] K^-T
+                        yl = (u * k3 + v * k4 + k5) * zm;
+                        if (stereo) {
+                            const float* kr = p.xr + (size_t)(grow % p.n_right) * 51;
+                            const float ur = __ldg(kr + j), vr = __ldg(kr + 17 + j);
+                            xd = xl - (ur * k0 + vr * k1 + k2) * zm;  // process.py:41 cat(l, l - r)
+                            yd = yl - (ur * k3 + vr * k4 + k5) * zm;
+                        } else if (p.flags & MLB_FWD_ZERO_CENTER) {
+                            xl -= cen[sr * 4 + 2];  // process.py:61-62
+                            yl -= cen[sr * 4 + 3];
+                        }
                     }
-                    uc = __fadd_rn(__fdiv_rn(__fsub_rn(umax, umin), 2.f), umin);
-                    vc = __fadd_rn(__fdiv_rn(__fsub_rn(vmax, vmin), 2.f), vmin);
-                }
-                cen[sr * 4 + 0] = uc;
-                cen[sr * 4 + 1] = vc;
-                cen[sr * 4 + 2] = (uc * k0 + vc * k1 + k2) * zm;
-                cen[sr * 4 + 3] = (uc * k3 + vc * k4 + k5) * zm;
-            }
-            if (p.flags & MLB_FWD_ZERO_CENTER) __syncthreads();
-            for (int idx = tid; idx < ROWS * 17; idx += nthreads) {
-                const int r = idx / 17, j = idx % 17, sr = smem_row(r, TM);
-                float xl = 0.f, yl = 0.f, xd = 0.f, yd = 0.f;
-                if (r < rows_here) {
-                    const int grow = row0 + r;
-                    const int li = stereo ? grow / p.n_right : grow;
-                    const float* kp = p.x + (size_t)li * 51;
-                    const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
-                    xl = (u * k0 + v * k1 + k2) * zm;  // camera.py:26-27, rows 0/1 of [u v 1] K^-T
-                    yl = (u * k3 + v * k4 + k5) * zm;
+                    xin[(2 * j) * MP + sr] = xl;
+                    xin[(2 * j + 1) * MP + sr] = yl;
                     if (stereo) {
-                        const float* kr = p.xr + (size_t)(grow % p.n_right) * 51;
-                        const float ur = __ldg(kr + j), vr = __ldg(kr + 17 + j);
-                        xd = xl - (ur * k0 + vr * k1 + k2) * zm;  // process.py:41 cat(l, l - r)
-                        yd = yl - (ur * k3 + vr * k4 + k5) * zm;
-                    } else if (p.flags & MLB_FWD_ZERO_CENTER) {
-                        xl -= cen[sr * 4 + 2];  // process.py:61-62
-                        yl -= cen[sr * 4 + 3];
+                        xin[(34 + 2 * j) * MP + sr] = xd;
+                        xin[(35 + 2 * j) * MP + sr] = yd;
                     }
                 }
-                xin[(2 * j) * MP + sr] = xl;
-                xin[(2 * j + 1) * MP + sr] = yl;
-                if (stereo) {
-                    xin[(34 + 2 * j) * MP + sr] = xd;
-                    xin[(35 + 2 * j) * MP + sr] = yd;
+            }
+            consumer_sync(nthreads);
+            if (p.out_x != nullptr && p.input_kind != MLB_IN_X) {
+                for (int idx = tid; idx < rows_here * p.in_size; idx += nthreads) {
+                    const int r = idx / p.in_size, k = idx % p.in_size;
+                    p.out_x[(size_t)(row0 + r) * p.in_size + k] = xin[k * MP + smem_row(r, TM)];
                 }
             }
-        }
-        __syncthreads();
-        if (p.out_x != nullptr && p.input_kind != MLB_IN_X) {
-            for (int idx = tid; idx < rows_here * p.in_size; idx += nthreads) {
-                const int r = idx / p.in_size, k = idx % p.in_size;
-                p.out_x[(size_t)(row0 + r) * p.in_size + k] = xin[k * MP + smem_row(r, TM)];
-            }
-        }
 
-        // -------------------------------------------------------------------- layer program
-        int site = 0;
-        for (int oi = 0; oi < p.n_ops; ++oi) {
-            const mlb_op& op = p.ops[oi];
-            if (op.type == MLB_OP_GEMM) {
-                const float* in = (op.flags & MLB_F_IN_XIN) ? xin : act;
-                const int nchunks = op.Kpad / KC;
-                float acc[TM][8];
-#pragma unroll
-                for (int i = 0; i < TM; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-                const float* a_ptr = in + g * 8;
-                for (int ch = 0; ch < nchunks; ++ch, ++q) {
-                    if (tid == 0) produce_upto(pr, q + NSTAGE, p, ring, full, empty, L);
-                    const unsigned stage = q % NSTAGE;
-                    mbar_wait(&full[stage], (q / NSTAGE) & 1, p.err_flag);
-                    const float* b_ptr = ring + (size_t)stage * KC * L + warp * 64 + c * 8;
-#pragma unroll
-                    for (int kk = 0; kk < KC; ++kk) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(a_ptr + (ch * KC + kk) * MP);
-                        const float4 a1 = *reinterpret_cast<const float4*>(a_ptr + (ch * KC + kk) * MP + 4);
-                        const float4 b0 = *reinterpret_cast<const float4*>(b_ptr + kk * L);
-                        const float4 b1 = *reinterpret_cast<const float4*>(b_ptr + kk * L + 4);
-                        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                        for (int i = 0; i < TM; ++i)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
-                }
-
-                // ---- epilogue: folded BatchNorm affine, ReLU, dropout, residual
-                const int n0 = warp * 64 + c * 8;
-                {
-                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + n0));
-                    const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + n0 + 4));
-                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + n0));
-                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + n0 + 4));
-                    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                    const bool relu = (op.flags & MLB_F_RELU) != 0;
+            // ---------------------------------------------------------------- layer program
+            int site = 0;
+            for (int oi = 0; oi < p.n_ops; ++oi) {
+                const mlb_op& op = p.ops[oi];
+                if (op.type == MLB_OP_GEMM) {
+                    const float* in = (op.flags & MLB_F_IN_XIN) ? xin : act;
+                    const int nchunks = op.Kpad / KC;
+                    float acc[TM][8];
 #pragma unroll
                     for (int i = 0; i < TM; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float v = fmaf(acc[i][j], sc[j], sh[j]);
-                            acc[i][j] = relu ? fmaxf(v, 0.f) : v;
-                        }
-                }
-                if (op.flags & MLB_F_DROPOUT) {
-                    if (p.flags & MLB_FWD_DROPOUT) {
-                        const float inv_keep = 1.0f / (1.0f - p.p_drop);
+                        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+                    const float* a_ptr = in + g * 16;
+                    for (int ch = 0; ch < nchunks; ++ch, ++q) {
+                        const unsigned stage = q % NSTAGE;
+                        mbar_wait(&full[stage], (q / NSTAGE) & 1, p.err_flag);
+                        const float* b_ptr = ring + (size_t)stage * KC * L + n0;
 #pragma unroll
-                        for (int i = 0; i < TM; ++i) {
-                            const int grow = row0 + g * TM + i;
+                        for (int kk = 0; kk < KC; ++kk) {
+                            float a[A4 * 4];
+#pragma unroll
+                            for (int v = 0; v < A4; ++v) {
+                                const float4 t = *reinterpret_cast<const float4*>(a_ptr + (ch * KC + kk) * MP + v * 4);
+                                a[v * 4 + 0] = t.x, a[v * 4 + 1] = t.y, a[v * 4 + 2] = t.z, a[v * 4 + 3] = t.w;
+                            }
+                            const float4 b0 = *reinterpret_cast<const float4*>(b_ptr + kk * L);
+                            const float4 b1 = *reinterpret_cast<const float4*>(b_ptr + kk * L + 64);
+                            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[stage]);
+                    }
+
+                    // ---- epilogue: folded BatchNorm affine, ReLU, dropout, residual
+                    {
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + n0));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + n0 + 64));
+                        const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + n0));
+                        const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + n0 + 64));
+                        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                        const bool relu = (op.flags & MLB_F_RELU) != 0;
+#pragma unroll
+                        for (int i = 0; i < TM; ++i)
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                bool keep;
-                                if (p.drop_mask != nullptr)
-                                    keep = grow < p.n_rows
-                                               ? p.drop_mask[((size_t)site * p.n_rows + grow) * L + n0 + j] != 0
-                                               : true;
-                                else
-                                    keep = keep_draw(p.drop_seed, site, grow, n0 + j, p.p_drop);
-                                acc[i][j] = keep ? acc[i][j] * inv_keep : 0.f;
+                                float v = fmaf(acc[i][j], sc[j], sh[j]);
+                                acc[i][j] = relu ? fmaxf(v, 0.f) : v;
+                            }
+                    }
+                    if (op.flags & MLB_F_DROPOUT) {
+                        if (p.flags & MLB_FWD_DROPOUT) {
+                            const float inv_keep = 1.0f / (1.0f - p.p_drop);
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) {
+                                const int grow = row0 + g * TM + i;
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int n = n0 + (j & 3) + (j >> 2) * 64;
+                                    bool keep;
+                                    if (p.drop_mask != nullptr)
+                                        keep = grow < p.n_rows ? p.drop_mask[((size_t)site * p.n_rows + grow) * L + n] != 0 : true;
+                                    else
+                                        keep = keep_draw(p.drop_seed, site, grow, n, p.p_drop);
+                                    acc[i][j] = keep ? acc[i][j] * inv_keep : 0.f;
+                                }
                             }
                         }
+                        site++;
                     }
-                    site++;
-                }
-                if (op.flags & MLB_F_ADD_RES) {
-                    if (res_tmem) {
+                    if (op.flags & MLB_F_ADD_RES) {
+                        if (res_tmem) {
 #pragma unroll
-                        for (int i = 0; i < TM; ++i) {
-                            float r[8];
-                            tmem_ld8(tmem_base + i * 8, r);
+                            for (int i = 0; i < TM; ++i) {
+                                float r[8];
+                                tmem_ld8(tmem_base + i * 8, r);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[i][j] += r[j];
+                                for (int j = 0; j < 8; ++j) acc[i][j] += r[j];
+                            }
+                        } else {
+                            const float* rs = p.res_scratch + (size_t)blockIdx.x * (128 * RES_STRIDE) + tid;
+#pragma unroll
+                            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[i][j] += rs[(i * 8 + j) * RES_STRIDE];
                         }
-                    } else {
-                        const float* rs = p.res_scratch + (size_t)blockIdx.x * 64 * nthreads + tid;
-#pragma unroll
-                        for (int i = 0; i < TM; ++i)
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[i][j] += rs[(size_t)(i * 8 + j) * nthreads];
                     }
-                }
-                if (op.flags & MLB_F_SAVE_RES) {
-                    if (res_tmem) {
+                    if (op.flags & MLB_F_SAVE_RES) {
+                        if (res_tmem) {
 #pragma unroll
-                        for (int i = 0; i < TM; ++i) tmem_st8(tmem_base + i * 8, acc[i]);
-                        tmem_st_wait();
-                    } else {
-                        float* rs = p.res_scratch + (size_t)blockIdx.x * 64 * nthreads + tid;
+                            for (int i = 0; i < TM; ++i) tmem_st8(tmem_base + i * 8, acc[i]);
+                            tmem_st_wait();
+                        } else {
+                            float* rs = p.res_scratch + (size_t)blockIdx.x * (128 * RES_STRIDE) + tid;
 #pragma unroll
-                        for (int i = 0; i < TM; ++i)
+                            for (int i = 0; i < TM; ++i)
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) rs[(size_t)(i * 8 + j) * nthreads] = acc[i][j];
+                                for (int j = 0; j < 8; ++j) rs[(i * 8 + j) * RES_STRIDE] = acc[i][j];
+                        }
                     }
-                }
-                __syncthreads();  // every warp has finished reading `act` as this layer's input
+                    consumer_sync(nthreads);  // every warp has finished reading `act` as this layer's input
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 lo, hi;
-                    lo.x = acc[0][j];
-                    lo.y = TM > 1 ? acc[TM > 1 ? 1 : 0][j] : 0.f;
-                    lo.z = TM > 2 ? acc[TM > 2 ? 2 : 0][j] : 0.f;
-                    lo.w = TM > 3 ? acc[TM > 3 ? 3 : 0][j] : 0.f;
-                    hi.x = TM > 4 ? acc[TM > 4 ? 4 : 0][j] : 0.f;
-                    hi.y = TM > 5 ? acc[TM > 5 ? 5 : 0][j] : 0.f;
-                    hi.z = TM > 6 ? acc[TM > 6 ? 6 : 0][j] : 0.f;
-                    hi.w = TM > 7 ? acc[TM > 7 ? 7 : 0][j] : 0.f;
-                    *reinterpret_cast<float4*>(act + (size_t)(n0 + j) * MP + g * 8) = lo;
-                    *reinterpret_cast<float4*>(act + (size_t)(n0 + j) * MP + g * 8 + 4) = hi;
-                }
-                __syncthreads();
-            } else {
-                // ---- narrow head: one warp per output column, lane = tile row
-                for (int o = nwarps - 1 - warp; o < op.N; o += nwarps) {
-                    const float* w = p.blob + op.w_off + (size_t)o * op.K;
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    for (int k = 0; k < op.K; k += 4) {
-                        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
-                        a0 = fmaf(act[(k + 0) * MP + lane], wv.x, a0);
-                        a1 = fmaf(act[(k + 1) * MP + lane], wv.y, a1);
-                        a2 = fmaf(act[(k + 2) * MP + lane], wv.z, a2);
-                        a3 = fmaf(act[(k + 3) * MP + lane], wv.w, a3);
+                    for (int j = 0; j < 8; ++j) {
+                        float* dst = act + (size_t)(n0 + (j & 3) + (j >> 2) * 64) * MP + g * 16;
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) {
+                            float4 t;
+                            t.x = (v * 4 + 0 < TM) ? acc[v * 4 + 0 < TM ? v * 4 + 0 : 0][j] : 0.f;
+                            t.y = (v * 4 + 1 < TM) ? acc[v * 4 + 1 < TM ? v * 4 + 1 : 0][j] : 0.f;
+                            t.z = (v * 4 + 2 < TM) ? acc[v * 4 + 2 < TM ? v * 4 + 2 : 0][j] : 0.f;
+                            t.w = (v * 4 + 3 < TM) ? acc[v * 4 + 3 < TM ? v * 4 + 3 : 0][j] : 0.f;
+                            *reinterpret_cast<float4*>(dst + v * 4) = t;
+                        }
                     }
-                    outs[lane * OUT_LD + op.out_col + o] = ((a0 + a1) + (a2 + a3)) + __ldg(p.blob + op.shift_off + o);
+                    consumer_sync(nthreads);
+                } else {
+                    // ---- narrow head: one warp per output column, lane = tile row slot
+                    for (int o = nwarps - 1 - warp; o < op.N; o += nwarps) {
+                        const float* w = p.blob + op.w_off + (size_t)o * op.K;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                        for (int k = 0; k < op.K; k += 4) {
+                            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+                            a0 = fmaf(act[(k + 0) * MP + lane], wv.x, a0);
+                            a1 = fmaf(act[(k + 1) * MP + lane], wv.y, a1);
+                            a2 = fmaf(act[(k + 2) * MP + lane], wv.z, a2);
+                            a3 = fmaf(act[(k + 3) * MP + lane], wv.w, a3);
+                        }
+                        outs[lane * OUT_LD + op.out_col + o] = ((a0 + a1) + (a2 + a3)) + __ldg(p.blob + op.shift_off + o);
+                    }
                 }
             }
-        }
-        __syncthreads();
+            consumer_sync(nthreads);
 
-        // -------------------------------------------------------------------- decode + store (one thread per row)
-        if (tid < MP) {
-            const int sr = tid, grp = sr >> 3, i = sr & 7;
-            const int r = grp * TM + i;
-            if (i < TM && r < rows_here) {
-                const size_t grow = (size_t)row0 + r;
-                const float* o = outs + sr * OUT_LD;
-                for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
-                float x = 0.f, y = 0.f, z = 0.f, d = 0.f, bi = 0.f, yaw_p = 0.f, yaw_o = 0.f, aux = 0.f;
-                if (p.decode_kind == MLB_DECODE_LOCO) {
-                    const float th = o[0], ps = o[1];
-                    d = o[2];
-                    bi = __fmul_rn(expf(o[3]), d);                       // process.py:132
-                    x = __fmul_rn(__fmul_rn(d, sinf(ps)), cosf(th));     // camera.py:232
-                    y = __fmul_rn(d, cosf(ps));                          // camera.py:236
-                    z = sqrtf(__fsub_rn(__fsub_rn(__fmul_rn(d, d), __fmul_rn(x, x)), __fmul_rn(y, y)));  // process.py:265
-                    yaw_p = atan2f(o[7], o[8]);                          // process.py:272
-                    if (p.out_size == 10) aux = 1.0f / (1.0f + expf(-o[9]));  // process.py:277
-                } else if (p.decode_kind == MLB_DECODE_MONO) {
-                    x = o[0], y = o[1], z = o[2];
-                    d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // process.py:350
-                    bi = __fmul_rn(expf(o[3]), o[2]);
-                    yaw_p = atan2f(o[7], o[8]);
-                } else if (p.decode_kind == MLB_DECODE_DB) {
-                    d = o[0];
-                    bi = __fmul_rn(expf(o[1]), o[0]);  // net.py:98
-                }
-                if (p.decode_kind == MLB_DECODE_LOCO || p.decode_kind == MLB_DECODE_MONO) {
-                    yaw_o = __fadd_rn(yaw_p, atan2f(x, z));  // camera.py:203-204
-                    if (yaw_o > 3.14159265358979323846f) yaw_o = __fsub_rn(yaw_o, 6.28318530717958647692f);
-                    if (yaw_o < -3.14159265358979323846f) yaw_o = __fadd_rn(yaw_o, 6.28318530717958647692f);
-                }
-                if (p.out_dec != nullptr) {
-                    float4* dst = reinterpret_cast<float4*>(p.out_dec + grow * 8);
-                    dst[0] = make_float4(x, y, z, d);
-                    dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
-                }
-                if (p.out_xyzc != nullptr && p.input_kind == MLB_IN_KPS) {
-                    // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
-                    const float uc = cen[sr * 4 + 0], vc = cen[sr * 4 + 1];
-                    const float cx = uc * p.kinv[0] + vc * p.kinv[1] + p.kinv[2];
-                    const float cy = uc * p.kinv[3] + vc * p.kinv[4] + p.kinv[5];
-                    const float cz = uc * p.kinv[6] + vc * p.kinv[7] + p.kinv[8];
-                    const float den = sqrtf(__fadd_rn(__fadd_rn(1.f, __fmul_rn(cx, cx)), __fmul_rn(cy, cy)));
-                    const float px = __fdiv_rn(__fmul_rn(cx, d), den), py = __fdiv_rn(__fmul_rn(cy, d), den),
-                                pz = __fdiv_rn(__fmul_rn(cz, d), den);
-                    const float nrm = sqrtf(px * px + py * py + pz * pz);
-                    *reinterpret_cast<float4*>(p.out_xyzc + grow * 4) = make_float4(px, py, pz, nrm);
+            // ---------------------------------------------------------------- decode + store (one thread per row)
+            if (tid < MP) {
+                const int sr = tid, grp = sr >> 4, i = sr & 15;
+                const int r = grp * TM + i;
+                if (i < TM && r < rows_here) {
+                    const size_t grow = (size_t)row0 + r;
+                    const float* o = outs + sr * OUT_LD;
+                    for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
+                    float x = 0.f, y = 0.f, z = 0.f, d = 0.f, bi = 0.f, yaw_p = 0.f, yaw_o = 0.f, aux = 0.f;
+                    if (p.decode_kind == MLB_DECODE_LOCO) {
+                        const float th = o[0], ps = o[1];
+                        d = o[2];
+                        bi = __fmul_rn(expf(o[3]), d);                    // process.py:132
+                        x = __fmul_rn(__fmul_rn(d, sinf(ps)), cosf(th));  // camera.py:232
+                        y = __fmul_rn(d, cosf(ps));                       // camera.py:236
+                        z = sqrtf(__fsub_rn(__fsub_rn(__fmul_rn(d, d), __fmul_rn(x, x)), __fmul_rn(y, y)));  // process.py:265
+                        yaw_p = atan2f(o[7], o[8]);                       // process.py:272
+                        if (p.out_size == 10) aux = 1.0f / (1.0f + expf(-o[9]));  // process.py:277
+                    } else if (p.decode_kind == MLB_DECODE_MONO) {
+                        x = o[0], y = o[1], z = o[2];
+                        d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // process.py:350
+                        bi = __fmul_rn(expf(o[3]), o[2]);
+                        yaw_p = atan2f(o[7], o[8]);
+                    } else if (p.decode_kind == MLB_DECODE_DB) {
+                        d = o[0];
+                        bi = __fmul_rn(expf(o[1]), o[0]);  // net.py:98
+                    }
+                    if (p.decode_kind == MLB_DECODE_LOCO || p.decode_kind == MLB_DECODE_MONO) {
+                        yaw_o = __fadd_rn(yaw_p, atan2f(x, z));  // camera.py:203-204
+                        if (yaw_o > 3.14159265358979323846f) yaw_o = __fsub_rn(yaw_o, 6.28318530717958647692f);
+                        if (yaw_o < -3.14159265358979323846f) yaw_o = __fadd_rn(yaw_o, 6.28318530717958647692f);
+                    }
+                    if (p.out_dec != nullptr) {
+                        float4* dst = reinterpret_cast<float4*>(p.out_dec + grow * 8);
+                        dst[0] = make_float4(x, y, z, d);
+                        dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
+                    }
+                    if (p.out_xyzc != nullptr && p.input_kind == MLB_IN_KPS) {
+                        // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
+                        const float uc = cen[sr * 4 + 0], vc = cen[sr * 4 + 1];
+                        const float cx = uc * p.kinv[0] + vc * p.kinv[1] + p.kinv[2];
+                        const float cy = uc * p.kinv[3] + vc * p.kinv[4] + p.kinv[5];
+                        const float cz = uc * p.kinv[6] + vc * p.kinv[7] + p.kinv[8];
+                        const float den = sqrtf(__fadd_rn(__fadd_rn(1.f, __fmul_rn(cx, cx)), __fmul_rn(cy, cy)));
+                        const float px = __fdiv_rn(__fmul_rn(cx, d), den), py = __fdiv_rn(__fmul_rn(cy, d), den),
+                                    pz = __fdiv_rn(__fmul_rn(cz, d), den);
+                        const float nrm = sqrtf(px * px + py * py + pz * pz);
+                        *reinterpret_cast<float4*>(p.out_xyzc + grow * 4) = make_float4(px, py, pz, nrm);
+                    }
                 }
             }
+            consumer_sync(nthreads);
         }
-        __syncthreads();
+        }  // active consumer warp
     }
 
-    if (res_tmem) {
-        tmem_fence_before();
-        __syncthreads();
-        if (warp == 0) tmem_dealloc(*tmem_slot, tmem_cols);
-    }
+    if (res_tmem) tmem_fence_before();
+    __syncthreads();
+    if (res_tmem && warp == 0) tmem_dealloc(*tmem_slot, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,6 +517,30 @@ __global__ void __launch_bounds__(512) ffma_probe_kernel(int iters, float* sink)
     if (s == 123.456f) sink[0] = s;
 }
 
+// packed variant: fma.rn.f32x2 (SASS FFMA2), 2 FMAs per lane per instruction
+__global__ void __launch_bounds__(512) ffma2_probe_kernel(int iters, float* sink) {
+    unsigned long long a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float lo = (float)(threadIdx.x + i) * 1e-3f, hi = lo + 0.5f;
+        a[i] = ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+    }
+    const float bf = 1.0000001f, cf = 1e-7f * (float)blockIdx.x;
+    const unsigned long long b = ((unsigned long long)__float_as_uint(bf) << 32) | __float_as_uint(bf);
+    const unsigned long long cc = ((unsigned long long)__float_as_uint(cf) << 32) | __float_as_uint(cf);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(cc));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += __uint_as_float((unsigned)a[i]) + __uint_as_float((unsigned)(a[i] >> 32));
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace mlb
 
 // ================================================================================================
@@ -571,7 +599,7 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     if (desc->abi_version != MLB_ABI_VERSION) return fail("mlb_create: ABI version mismatch");
     if (desc->n_ops < 1 || desc->n_ops > MLB_MAX_OPS) return fail("mlb_create: n_ops out of range");
     const int L = desc->linear_size;
-    if (L < 64 || L > 1024 || (L % 64) != 0) return fail("mlb_create: linear_size must be a multiple of 64 in [64,1024]");
+    if (L < 128 || L > 1024 || (L % 128) != 0) return fail("mlb_create: linear_size must be a multiple of 128 in [128,1024]");
     if (desc->input_size < 1 || desc->input_size > KIN_MAX) return fail("mlb_create: input_size must be in [1,68]");
     if (desc->output_size < 1 || desc->output_size > OUT_LD) return fail("mlb_create: output_size must be in [1,16]");
     for (int i = 0; i < desc->n_ops; ++i) {
@@ -604,7 +632,7 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     m->n_floats = n_floats;
     CU(cudaMalloc(&m->blob_dev, n_floats * sizeof(float)));
     CU(cudaMemcpy(m->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
-    m->res_floats = (size_t)m->n_sms * 4 * 64 * MAX_THREADS;  // up to 4 resident CTAs per SM for narrow models
+    m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
     CU(cudaMalloc(&m->err_flag_dev, sizeof(int)));
     CU(cudaMemset(m->err_flag_dev, 0, sizeof(int)));
@@ -637,10 +665,10 @@ extern "C" void mlb_destroy(mlb_handle h) {
 
 static int pick_rows_per_group(int n_rows, int n_ctas) {
     // minimise waves(tm) * tm  (time ~ rows per CTA per wave), prefer the larger tile on ties
-    int best = 8;
+    int best = 16;
     long best_cost = -1;
-    for (int tm = 8; tm >= 4; --tm) {
-        const long tiles = (n_rows + 4 * tm - 1) / (4 * tm);
+    for (int tm = 16; tm >= 8; tm -= 2) {
+        const long tiles = (n_rows + 2 * tm - 1) / (2 * tm);
         const long waves = (tiles + n_ctas - 1) / n_ctas;
         const long cost = waves * tm;
         if (best_cost < 0 || cost < best_cost) best_cost = cost, best = tm;
@@ -701,28 +729,29 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     p.res_scratch = h->res_scratch;
     p.err_flag = h->err_flag_dev;
 
-    const int threads = d.linear_size / 2;  // one warp per 64 hidden columns
+    // consumer warpgroups (one active warp per 128 hidden columns) + one producer warpgroup (setmaxnreg split)
+    const int threads = ((d.linear_size / 128 + 3) / 4) * 128 + 128;
     const size_t smem = fwd_smem_bytes(d.linear_size);
     int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 4) ctas_per_sm = 4;
-    if (ctas_per_sm > 2048 / threads) ctas_per_sm = 2048 / threads;
+    if (ctas_per_sm > 65536 / (threads * 168)) ctas_per_sm = 65536 / (threads * 168) > 0 ? 65536 / (threads * 168) : 1;
     if (a->flags & MLB_FWD_RES_TMEM) ctas_per_sm = ctas_per_sm > 2 ? 2 : ctas_per_sm;
     const int max_ctas = h->n_sms * ctas_per_sm;
     int tm = a->rows_per_group;
     if (tm == 0) tm = pick_rows_per_group(a->n_rows, max_ctas);
-    if (tm < 4 || tm > 8) return fail("mlb_forward: rows_per_group must be 0 or 4..8");
-    p.n_tiles = (a->n_rows + 4 * tm - 1) / (4 * tm);
+    if (tm < 8 || tm > 16 || (tm & 1)) return fail("mlb_forward: rows_per_group must be 0 or one of 8,10,12,14,16");
+    p.n_tiles = (a->n_rows + 2 * tm - 1) / (2 * tm);
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-    if ((size_t)grid * 64 * threads > h->res_floats) return fail("mlb_forward: residual scratch too small");
+    if ((size_t)grid * 128 * 256 > h->res_floats) return fail("mlb_forward: residual scratch too small");
 
     cudaError_t e;
     switch (tm) {
-        case 4: e = launch_fwd<4>(p, grid, threads, smem, st); break;
-        case 5: e = launch_fwd<5>(p, grid, threads, smem, st); break;
-        case 6: e = launch_fwd<6>(p, grid, threads, smem, st); break;
-        case 7: e = launch_fwd<7>(p, grid, threads, smem, st); break;
-        default: e = launch_fwd<8>(p, grid, threads, smem, st); break;
+        case 8: e = launch_fwd<8>(p, grid, threads, smem, st); break;
+        case 10: e = launch_fwd<10>(p, grid, threads, smem, st); break;
+        case 12: e = launch_fwd<12>(p, grid, threads, smem, st); break;
+        case 14: e = launch_fwd<14>(p, grid, threads, smem, st); break;
+        default: e = launch_fwd<16>(p, grid, threads, smem, st); break;
     }
     if (e != cudaSuccess) return fail(std::string("loco_forward_kernel launch: ") + cudaGetErrorString(e));
     g_launches++;
@@ -817,8 +846,12 @@ extern "C" int mlb_probe_ffma(int device, int blocks, int iters, double* flops, 
     CU(cudaSetDevice(device));
     static float* sink = nullptr;
     if (!sink) CU(cudaMalloc(&sink, 16));
-    ffma_probe_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(iters, sink);
+    if (iters < 0)
+        ffma2_probe_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(-iters, sink);  // packed fma.rn.f32x2 variant
+    else
+        ffma_probe_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(iters, sink);
     CU(cudaGetLastError());
+    if (iters < 0) iters = -iters;
     g_launches++;
     if (flops) *flops = (double)blocks * 512.0 * (double)iters * 8.0 * 16.0 * 2.0;
     return 0;

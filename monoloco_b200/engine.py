@@ -190,7 +190,7 @@ def preprocess_device(kps, kk, zero_center=False):
     return out
 
 
-def probe_ffma_tflops(device_index=0, iters=4096, reps=5):
+def probe_ffma_tflops(device_index=0, iters=4096, reps=5, packed=False):
     """Measured FP32-FFMA throughput of this GPU (roofline denominator in the fp32-bound regime)."""
     lib = L_.lib()
     n_sm = torch.cuda.get_device_properties(device_index).multi_processor_count
@@ -201,7 +201,8 @@ def probe_ffma_tflops(device_index=0, iters=4096, reps=5):
     for _ in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        L_.check(lib.mlb_probe_ffma(device_index, blocks, iters, C.byref(flops), C.c_void_p(st.cuda_stream)), 'probe')
+        L_.check(lib.mlb_probe_ffma(device_index, blocks, -iters if packed else iters, C.byref(flops),
+                                    C.c_void_p(st.cuda_stream)), 'probe')
         e1.record(st)
         e1.synchronize()
         best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)

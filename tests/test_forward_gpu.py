@@ -76,7 +76,7 @@ def test_forward_batches_vs_oracle(mono1024, B):
     _check_dec(O, out['dec'].cpu().numpy(), O.extract_outputs(ref), False)
 
 
-@pytest.mark.parametrize('tm', [4, 5, 6, 7, 8])
+@pytest.mark.parametrize('tm', [8, 10, 12, 14, 16])
 def test_forward_tile_shapes(mono1024, tm):
     """Every rows-per-group instantiation gives the same answer (ragged last tile included)."""
     O, synthetic, engine, L_ = _mods()
@@ -161,7 +161,7 @@ def test_stereo_pairs_and_filter():
 def test_stereo_kat_diagonal():
     O, synthetic, engine, L_ = _mods()
     f = np.load(os.path.join(GOLDEN, 'kat_stereo_val.npz'))
-    sd = synthetic.make_state_dict('loco', 68, 10, 64, 1, 6)
+    sd = synthetic.make_state_dict('loco', 68, 10, 128, 1, 6)
     eng = engine.LocoEngine(sd)
     for k in np.unique(f['K'].reshape(-1, 9), axis=0):
         rows = np.where((f['K'].reshape(-1, 9) == k).all(1))[0]
