@@ -8,9 +8,9 @@
 namespace mlb {
 
 constexpr int MP = 32;        // detection rows per CTA tile as laid out in shared memory (2 groups x 16)
-constexpr int KC = 4;         // k-steps per weight chunk (one TMA bulk copy = KC * L floats)
-constexpr int NSTAGE = 4;     // weight-ring depth
-constexpr int KIN_MAX = 68;   // largest network input (monstereo)
+constexpr int KC = 8;         // k-steps per weight chunk (one TMA bulk copy = KC * L floats = 32 KB at L = 1024)
+constexpr int NSTAGE = 3;     // weight-ring depth
+constexpr int KIN_MAX = 72;   // largest network input (monstereo, 68) rounded up to the chunk depth
 constexpr int OUT_LD = 16;    // raw-output staging row stride (output_size <= 16)
 constexpr int MAX_THREADS = 384;   // 2 consumer warpgroups + 1 producer warpgroup (setmaxnreg 240 / 24)
 
@@ -43,11 +43,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps with an error flag instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 24)) {
+            if (err_flag) atomicExch(err_flag, ERR_MBAR_TIMEOUT);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+// Producer-side wait: sleeps between polls (the ring is normally full, so this warp mostly waits).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int* err_flag) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(128);
+        if (++spins > (1u << 22)) {
             if (err_flag) atomicExch(err_flag, ERR_MBAR_TIMEOUT);
             __threadfence_system();
             __trap();
@@ -92,6 +116,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- packed fp32x2 math (sm_100: fma.rn.f32x2 -> SASS FFMA2), IEEE fma per half: bit-identical to two fmaf
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 
 // ---- counter-based RNG for the MC-dropout keep mask (net.py:135-161) ----

@@ -63,7 +63,7 @@ __device__ __forceinline__ void consumer_sync(int n_consumer_threads) {
 
 // The weight stream: every GEMM chunk of every tile this CTA owns, in consumption order.
 __device__ __forceinline__ void producer_loop(const FwdParams& p, float* ring, uint64_t* full, uint64_t* empty, int L) {
-    unsigned q = 0;
+    unsigned q = 0, stage = 0, parity = 0;  // parity of the fill this iteration performs on `stage`
     const uint32_t bytes = (uint32_t)(KC * L * sizeof(float));
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -72,10 +72,10 @@ __device__ __forceinline__ void producer_loop(const FwdParams& p, float* ring, u
             const float* src = p.blob + op.w_off;
             const int nchunks = op.Kpad / KC;
             for (int ch = 0; ch < nchunks; ++ch, ++q) {
-                const unsigned stage = q % NSTAGE;
-                if (q >= NSTAGE) mbar_wait(&empty[stage], ((q / NSTAGE) - 1) & 1, p.err_flag);
+                if (q >= NSTAGE) mbar_wait_backoff(&empty[stage], parity ^ 1, p.err_flag);  // consumers released fill #(q/NSTAGE - 1)
                 mbar_expect_tx(&full[stage], bytes);
                 tma_bulk_g2s(ring + (size_t)stage * KC * L, src + (size_t)ch * KC * L, bytes, &full[stage]);
+                if (++stage == NSTAGE) stage = 0, parity ^= 1;
             }
         }
     }
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
     constexpr int RES_STRIDE = 256;   // residual scratch: [cta][TM*8][256 consumer threads], thread-private
 
     float* act = reinterpret_cast<float*>(smem_raw);  // [L][MP]
-    float* xin = act + (size_t)L * MP;                 // [KIN_MAX][MP]
-    float* outs = xin + KIN_MAX * MP;                  // [MP][OUT_LD]
+    float* xin = act;                                  // network input tile [kpad0][MP]: dead once w1's epilogue writes act
+    float* outs = act + (size_t)L * MP;                // [MP][OUT_LD]
     float* cen = outs + MP * OUT_LD;                   // [MP][4]  (u_c, v_c, cx*z_met, cy*z_met)
     float* ring = cen + MP * 4;                        // [NSTAGE][KC][L]
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTAGE * KC * L);
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
     const bool res_tmem = (p.flags & MLB_FWD_RES_TMEM) != 0;
     const uint32_t tmem_cols = nwarps <= 1 ? 128u : (nwarps <= 4 ? 128u : 256u);
 
-    for (int i = tid; i < L * MP + KIN_MAX * MP + MP * OUT_LD + MP * 4; i += blockDim.x) act[i] = 0.f;
+    for (int i = tid; i < L * MP + MP * OUT_LD + MP * 4; i += blockDim.x) act[i] = 0.f;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
@@ -132,6 +132,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
         uint32_t tmem_base = 0;
         if (res_tmem) tmem_base = *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
         unsigned q = 0;  // chunks consumed so far (identical in every consumer warp)
+        unsigned stage = 0, parity = 0;
+        unsigned total_chunks = 0;
+        for (int oi = 0; oi < p.n_ops; ++oi)
+            if (p.ops[oi].type == MLB_OP_GEMM) total_chunks += p.ops[oi].Kpad / KC;
+        total_chunks *= (unsigned)((p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+        mbar_wait(&full[0], 0, p.err_flag);  // chunk 0
         const float zm = p.z_met;
         const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
         // this thread's 8 output columns: n0 + {0..3} and n0 + 64 + {0..3}
@@ -216,36 +222,55 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 if (op.type == MLB_OP_GEMM) {
                     const float* in = (op.flags & MLB_F_IN_XIN) ? xin : act;
                     const int nchunks = op.Kpad / KC;
-                    float acc[TM][8];
+                    // accumulators as packed f32x2 pairs over two consecutive rows (lo = row 2*ip, hi = row 2*ip + 1):
+                    // fma.rn.f32x2 (SASS FFMA2) does both rows in one issue slot, so 2 warps/SMSP keep the FMA pipe fed
+                    unsigned long long acc2[TM / 2][8];
 #pragma unroll
-                    for (int i = 0; i < TM; ++i)
+                    for (int i = 0; i < TM / 2; ++i)
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+                        for (int j = 0; j < 8; ++j) acc2[i][j] = 0ull;
 
                     const float* a_ptr = in + g * 16;
                     for (int ch = 0; ch < nchunks; ++ch, ++q) {
-                        const unsigned stage = q % NSTAGE;
-                        mbar_wait(&full[stage], (q / NSTAGE) & 1, p.err_flag);
+                        // invariant: chunk q has landed (waited for at the end of the previous iteration).
+                        // Probe the NEXT stage now, non-blocking, so the mbarrier round trip hides under this chunk's FFMAs.
+                        unsigned nstage = stage + 1, nparity = parity;
+                        if (nstage == NSTAGE) nstage = 0, nparity ^= 1;
+                        const bool has_next = q + 1 < total_chunks;
+                        const bool next_ready = has_next ? mbar_test_wait(&full[nstage], nparity) : true;
                         const float* b_ptr = ring + (size_t)stage * KC * L + n0;
 #pragma unroll
                         for (int kk = 0; kk < KC; ++kk) {
-                            float a[A4 * 4];
+                            unsigned long long a2[(TM + 1) / 2];
+                            const float* ap = a_ptr + (ch * KC + kk) * MP;
 #pragma unroll
-                            for (int v = 0; v < A4; ++v) {
-                                const float4 t = *reinterpret_cast<const float4*>(a_ptr + (ch * KC + kk) * MP + v * 4);
-                                a[v * 4 + 0] = t.x, a[v * 4 + 1] = t.y, a[v * 4 + 2] = t.z, a[v * 4 + 3] = t.w;
+                            for (int v = 0; v < TM / 4; ++v) {
+                                const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(ap + v * 4);
+                                a2[v * 2 + 0] = t.x, a2[v * 2 + 1] = t.y;
                             }
+                            if (TM % 4) a2[(TM / 4) * 2] = *reinterpret_cast<const unsigned long long*>(ap + (TM / 4) * 4);
                             const float4 b0 = *reinterpret_cast<const float4*>(b_ptr + kk * L);
                             const float4 b1 = *reinterpret_cast<const float4*>(b_ptr + kk * L + 64);
                             const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                            for (int i = 0; i < TM; ++i)
+                            for (int j = 0; j < 8; ++j) {
+                                const unsigned long long bd = pack2(b[j], b[j]);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                                for (int i = 0; i < TM / 2; ++i) acc2[i][j] = ffma2(a2[i], bd, acc2[i][j]);
+                            }
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[stage]);
+                        if (!next_ready) mbar_wait(&full[nstage], nparity, p.err_flag);
+                        stage = nstage, parity = nparity;
                     }
+                    float acc[TM][8];
+#pragma unroll
+                    for (int i = 0; i < TM / 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            unpack2(acc2[i][j], acc[2 * i][j], acc[2 * i + 1][j]);
+                        }
 
                     // ---- epilogue: folded BatchNorm affine, ReLU, dropout, residual
                     {
@@ -334,6 +359,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                     for (int o = nwarps - 1 - warp; o < op.N; o += nwarps) {
                         const float* w = p.blob + op.w_off + (size_t)o * op.K;
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
                         for (int k = 0; k < op.K; k += 4) {
                             const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
                             a0 = fmaf(act[(k + 0) * MP + lane], wv.x, a0);
@@ -589,7 +615,7 @@ extern "C" uint64_t mlb_launch_count(void) { return g_launches.load(); }
 extern "C" int mlb_num_sms(mlb_handle h) { return h ? h->n_sms : 0; }
 
 static size_t fwd_smem_bytes(int L) {
-    size_t fl = (size_t)L * MP + KIN_MAX * MP + MP * OUT_LD + MP * 4 + (size_t)NSTAGE * KC * L;
+    size_t fl = (size_t)L * MP + MP * OUT_LD + MP * 4 + (size_t)NSTAGE * KC * L;
     return fl * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 16;
 }
 
@@ -600,7 +626,7 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     if (desc->n_ops < 1 || desc->n_ops > MLB_MAX_OPS) return fail("mlb_create: n_ops out of range");
     const int L = desc->linear_size;
     if (L < 128 || L > 1024 || (L % 128) != 0) return fail("mlb_create: linear_size must be a multiple of 128 in [128,1024]");
-    if (desc->input_size < 1 || desc->input_size > KIN_MAX) return fail("mlb_create: input_size must be in [1,68]");
+    if (desc->input_size < 1 || desc->input_size > 68) return fail("mlb_create: input_size must be in [1,68]");
     if (desc->output_size < 1 || desc->output_size > OUT_LD) return fail("mlb_create: output_size must be in [1,16]");
     for (int i = 0; i < desc->n_ops; ++i) {
         const mlb_op& op = ops[i];

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib as L_
 
-KC = 4          # must match csrc/common.cuh
+KC = 8          # must match csrc/common.cuh
 BN_EPS = 1e-5   # nn.BatchNorm1d default (architectures.py:25)
 ALIGN = 32      # floats (128 B): TMA bulk copies need 16 B, keep cache-line alignment
 
