@@ -98,7 +98,7 @@ typedef struct mlb_forward_args {
     float* out_raw;         /* [B, output_size]            required                                 */
     float* out_dec;         /* [B, 8] = x,y,z,d,bi,yaw_pred,yaw_orig,sigmoid(aux)   or NULL         */
     float* out_xyzc;        /* [B, 4] = xyz_from_distance(d, K^-1[u_c,v_c,1]) (camera.py:161-177,
-                               net.py:192-213) and its norm; MLB_IN_KPS only, or NULL               */
+                               net.py:192-213) and its norm; MLB_IN_KPS* (left pose), or NULL       */
     float* out_x;           /* [B, input_size] the pre-processed network input, or NULL             */
     const uint8_t* drop_mask; /* [sites][B][L] keep-mask (1 keep) for MLB_FWD_DROPOUT, or NULL      */
     uint64_t drop_seed;     /* in-kernel counter RNG seed when drop_mask == NULL                    */
@@ -118,10 +118,21 @@ int mlb_preprocess(const float* kps, int n_rows, const float kinv[9], float z_me
 
 /* monstereo arg-max filter (process.py:307-327): rows [n_left*n_right, out] viewed [n_left, n_right, out];
  * keeps, per left pose, every row whose last column >= the max over its right poses (ties kept, row-major
- * order).  Gathers raw (and dec/xyzc if non-NULL) rows into sel_*; writes the kept-row count to *n_sel_dev
+ * order).  Gathers raw (and dec / xyzc if non-NULL) rows into sel_*; writes the kept-row count to *n_sel_dev
  * and the kept flat row indices to sel_idx (capacity n_left*n_right).  Device buffers. */
-int mlb_stereo_filter(const float* raw, const float* dec, int n_left, int n_right, int out_size,
-                      float* sel_raw, float* sel_dec, int32_t* sel_idx, int32_t* n_sel_dev, void* stream);
+int mlb_stereo_filter(const float* raw, const float* dec, const float* xyzc, int n_left, int n_right, int out_size,
+                      float* sel_raw, float* sel_dec, float* sel_xyzc, int32_t* sel_idx, int32_t* n_sel_dev,
+                      void* stream);
+
+/* decode only (process.py:231-278 / 330-360 on a raw tensor that did not come from mlb_forward):
+ * raw [B, out_size] -> dec [B, 8] as in mlb_forward_args.out_dec.  Device buffers. */
+int mlb_decode(const float* raw, int n_rows, int out_size, int decode_kind, float* dec, void* stream);
+
+/* MC-dropout epistemic spread (net.py:135-161, process.py:101-122): d_bi [n_pass, n_rows, 2] = (d, bi) of
+ * n_pass stochastic forwards (MLB_FWD_DROPOUT); for every row draws n_samples Laplace(d, |bi|) samples per pass
+ * (counter RNG, `seed`) and writes the unbiased std over all n_pass*n_samples draws to out_std [n_rows]. */
+int mlb_laplace_std(const float* d_bi, int n_pass, int n_rows, int n_samples, uint64_t seed, float* out_std,
+                    void* stream);
 
 /* FP32-FFMA throughput probe (roofline denominator for the fp32-bound regime): every thread of
  * `blocks` x 512 threads runs |iters| x 128 FMAs in 16 independent chains (iters < 0: packed fma.rn.f32x2).

@@ -54,6 +54,49 @@ struct FwdParams {
     int* err_flag;
 };
 
+// Laplace / spherical / orientation decode of one raw output row (process.py:231-278, 330-360; net.py:95-100).
+// Explicit __f*_rn intrinsics pin the reference's operation order (no FMA contraction).
+__device__ __forceinline__ void decode_row(int kind, int out_size, const float* o, float& x, float& y, float& z, float& d,
+                                           float& bi, float& yaw_p, float& yaw_o, float& aux) {
+    x = y = z = d = bi = yaw_p = yaw_o = aux = 0.f;
+    if (kind == MLB_DECODE_LOCO) {
+        const float th = o[0], ps = o[1];
+        d = o[2];
+        bi = __fmul_rn(expf(o[3]), d);                    // process.py:132
+        x = __fmul_rn(__fmul_rn(d, sinf(ps)), cosf(th));  // camera.py:232
+        y = __fmul_rn(d, cosf(ps));                       // camera.py:236
+        z = sqrtf(__fsub_rn(__fsub_rn(__fmul_rn(d, d), __fmul_rn(x, x)), __fmul_rn(y, y)));  // process.py:265
+        yaw_p = atan2f(o[7], o[8]);                       // process.py:272
+        if (out_size == 10) aux = 1.0f / (1.0f + expf(-o[9]));  // process.py:277
+    } else if (kind == MLB_DECODE_MONO) {
+        x = o[0], y = o[1], z = o[2];
+        d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // process.py:350
+        bi = __fmul_rn(expf(o[3]), o[2]);
+        yaw_p = atan2f(o[7], o[8]);
+    } else if (kind == MLB_DECODE_DB) {
+        d = o[0];
+        bi = __fmul_rn(expf(o[1]), o[0]);  // net.py:98
+    }
+    if (kind == MLB_DECODE_LOCO || kind == MLB_DECODE_MONO) {
+        yaw_o = __fadd_rn(yaw_p, atan2f(x, z));  // camera.py:203-204
+        if (yaw_o > 3.14159265358979323846f) yaw_o = __fsub_rn(yaw_o, 6.28318530717958647692f);
+        if (yaw_o < -3.14159265358979323846f) yaw_o = __fadd_rn(yaw_o, 6.28318530717958647692f);
+    }
+}
+
+// stand-alone decode of a raw [B, out] tensor (extract_outputs on outputs that did not come from the fused kernel)
+__global__ void decode_kernel(const float* __restrict__ raw, int n_rows, int out_size, int kind, float* __restrict__ dec) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    float o[OUT_LD];
+    for (int k = 0; k < out_size; ++k) o[k] = raw[(size_t)row * out_size + k];
+    float x, y, z, d, bi, yaw_p, yaw_o, aux;
+    decode_row(kind, out_size, o, x, y, z, d, bi, yaw_p, yaw_o, aux);
+    float4* dst = reinterpret_cast<float4*>(dec + (size_t)row * 8);
+    dst[0] = make_float4(x, y, z, d);
+    dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
+}
+
 // local row r of a tile -> shared-memory row (2 groups of 16 slots, TM used per group)
 __device__ __forceinline__ int smem_row(int r, int tm) { return (r / tm) * 16 + (r % tm); }
 
@@ -158,12 +201,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 }
             } else {
                 const bool stereo = p.input_kind == MLB_IN_KPS_STEREO;
-                // bbox centre of the 17 keypoints (camera.py:82-86), mono only: zero-centering + xyz_from_distance ray
-                if (!stereo && tid < ROWS) {
+                // bbox centre of the (left) pose's 17 keypoints (camera.py:82-86): zero-centering + xyz_from_distance ray
+                if (tid < ROWS) {
                     const int r = tid, sr = smem_row(r, TM);
                     float uc = 0.f, vc = 0.f;
                     if (r < rows_here) {
-                        const float* kp = p.x + (size_t)(row0 + r) * 51;
+                        const float* kp = p.x + (size_t)(stereo ? (row0 + r) / p.n_right : (row0 + r)) * 51;
                         float umin = __ldg(kp), umax = umin, vmin = __ldg(kp + 17), vmax = vmin;
                         for (int j = 1; j < 17; ++j) {
                             const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
@@ -381,36 +424,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                     const size_t grow = (size_t)row0 + r;
                     const float* o = outs + sr * OUT_LD;
                     for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
-                    float x = 0.f, y = 0.f, z = 0.f, d = 0.f, bi = 0.f, yaw_p = 0.f, yaw_o = 0.f, aux = 0.f;
-                    if (p.decode_kind == MLB_DECODE_LOCO) {
-                        const float th = o[0], ps = o[1];
-                        d = o[2];
-                        bi = __fmul_rn(expf(o[3]), d);                    // process.py:132
-                        x = __fmul_rn(__fmul_rn(d, sinf(ps)), cosf(th));  // camera.py:232
-                        y = __fmul_rn(d, cosf(ps));                       // camera.py:236
-                        z = sqrtf(__fsub_rn(__fsub_rn(__fmul_rn(d, d), __fmul_rn(x, x)), __fmul_rn(y, y)));  // process.py:265
-                        yaw_p = atan2f(o[7], o[8]);                       // process.py:272
-                        if (p.out_size == 10) aux = 1.0f / (1.0f + expf(-o[9]));  // process.py:277
-                    } else if (p.decode_kind == MLB_DECODE_MONO) {
-                        x = o[0], y = o[1], z = o[2];
-                        d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // process.py:350
-                        bi = __fmul_rn(expf(o[3]), o[2]);
-                        yaw_p = atan2f(o[7], o[8]);
-                    } else if (p.decode_kind == MLB_DECODE_DB) {
-                        d = o[0];
-                        bi = __fmul_rn(expf(o[1]), o[0]);  // net.py:98
-                    }
-                    if (p.decode_kind == MLB_DECODE_LOCO || p.decode_kind == MLB_DECODE_MONO) {
-                        yaw_o = __fadd_rn(yaw_p, atan2f(x, z));  // camera.py:203-204
-                        if (yaw_o > 3.14159265358979323846f) yaw_o = __fsub_rn(yaw_o, 6.28318530717958647692f);
-                        if (yaw_o < -3.14159265358979323846f) yaw_o = __fadd_rn(yaw_o, 6.28318530717958647692f);
-                    }
+                    float x, y, z, d, bi, yaw_p, yaw_o, aux;
+                    decode_row(p.decode_kind, p.out_size, o, x, y, z, d, bi, yaw_p, yaw_o, aux);
                     if (p.out_dec != nullptr) {
                         float4* dst = reinterpret_cast<float4*>(p.out_dec + grow * 8);
                         dst[0] = make_float4(x, y, z, d);
                         dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
                     }
-                    if (p.out_xyzc != nullptr && p.input_kind == MLB_IN_KPS) {
+                    if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
                         // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
                         const float uc = cen[sr * 4 + 0], vc = cen[sr * 4 + 1];
                         const float cx = uc * p.kinv[0] + vc * p.kinv[1] + p.kinv[2];
@@ -469,8 +490,9 @@ __global__ void preprocess_kernel(const float* __restrict__ kps, int n_rows, flo
 // ------------------------------------------------------------------------------------------------
 // monstereo arg-max filter (process.py:307-327), single CTA: per-left max, tie mask, ordered compaction
 // ------------------------------------------------------------------------------------------------
-__global__ void stereo_filter_kernel(const float* __restrict__ raw, const float* __restrict__ dec, int n_left, int n_right,
-                                     int out_size, float* __restrict__ sel_raw, float* __restrict__ sel_dec,
+__global__ void stereo_filter_kernel(const float* __restrict__ raw, const float* __restrict__ dec,
+                                     const float* __restrict__ xyzc, int n_left, int n_right, int out_size,
+                                     float* __restrict__ sel_raw, float* __restrict__ sel_dec, float* __restrict__ sel_xyzc,
                                      int32_t* __restrict__ sel_idx, int32_t* __restrict__ n_sel) {
     extern __shared__ int sm_cnt[];  // [n_left + 1] kept rows per left pose -> exclusive prefix
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -516,10 +538,40 @@ __global__ void stereo_filter_kernel(const float* __restrict__ raw, const float*
                 for (int k = 0; k < out_size; ++k) sel_raw[(size_t)pos * out_size + k] = raw[src * out_size + k];
                 if (dec != nullptr && sel_dec != nullptr)
                     for (int k = 0; k < 8; ++k) sel_dec[(size_t)pos * 8 + k] = dec[src * 8 + k];
+                if (xyzc != nullptr && sel_xyzc != nullptr)
+                    for (int k = 0; k < 4; ++k) sel_xyzc[(size_t)pos * 4 + k] = xyzc[src * 4 + k];
                 pos++;
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MC-dropout epistemic spread (net.py:135-161 + process.py:101-122): for every detection, draw n_samples
+// Laplace(mu_n, |b_n|) samples for each of the n_pass stochastic forwards and return the unbiased std over all
+// n_pass * n_samples draws (torch: cat over passes -> .std(0)).  Inverse-CDF sampling with a counter RNG
+// (the reference reseeds torch's generator per pass: not reproducible here, equal in distribution).
+// ------------------------------------------------------------------------------------------------
+__global__ void laplace_std_kernel(const float* __restrict__ d_bi, int n_pass, int n_rows, int n_samples,
+                                   unsigned long long seed, float* __restrict__ out_std) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double mean = 0.0, m2 = 0.0;
+    long cnt = 0;
+    for (int n = 0; n < n_pass; ++n) {
+        const float mu = d_bi[((size_t)n * n_rows + row) * 2 + 0];
+        const float b = fabsf(d_bi[((size_t)n * n_rows + row) * 2 + 1]);  // process.py:105
+        for (int s = 0; s < n_samples; ++s) {
+            const uint32_t r = mix32((((uint64_t)row << 32) | ((uint64_t)n << 16) | (uint64_t)s) ^ (seed * 0x9E3779B97F4A7C15ULL));
+            const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f) - 0.5f;  // (-0.5, 0.5)
+            const float x = mu - b * copysignf(1.f, u) * log1pf(-2.f * fabsf(u));
+            ++cnt;
+            const double dlt = (double)x - mean;
+            mean += dlt / (double)cnt;
+            m2 += dlt * ((double)x - mean);
+        }
+    }
+    out_std[row] = cnt > 1 ? (float)sqrt(m2 / (double)(cnt - 1)) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -853,16 +905,39 @@ extern "C" int mlb_preprocess(const float* kps, int n_rows, const float kinv[9],
     return 0;
 }
 
-extern "C" int mlb_stereo_filter(const float* raw, const float* dec, int n_left, int n_right, int out_size, float* sel_raw,
-                                 float* sel_dec, int32_t* sel_idx, int32_t* n_sel_dev, void* stream) {
+extern "C" int mlb_stereo_filter(const float* raw, const float* dec, const float* xyzc, int n_left, int n_right, int out_size,
+                                 float* sel_raw, float* sel_dec, float* sel_xyzc, int32_t* sel_idx, int32_t* n_sel_dev,
+                                 void* stream) {
     if (!raw || !sel_raw || !sel_idx || !n_sel_dev || n_left < 1 || n_right < 1 || out_size < 1)
         return fail("mlb_stereo_filter: bad argument");
     const size_t smem = (size_t)(n_left + 1) * sizeof(int);
     if (smem > 200 * 1024) return fail("mlb_stereo_filter: too many left poses for one CTA");
     if (smem > 48 * 1024)
         CU(cudaFuncSetAttribute(stereo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stereo_filter_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(raw, dec, n_left, n_right, out_size, sel_raw, sel_dec, sel_idx,
-                                                                 n_sel_dev);
+    stereo_filter_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(raw, dec, xyzc, n_left, n_right, out_size, sel_raw, sel_dec,
+                                                                 sel_xyzc, sel_idx, n_sel_dev);
+    CU(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+extern "C" int mlb_decode(const float* raw, int n_rows, int out_size, int decode_kind, float* dec, void* stream) {
+    if (n_rows == 0) return 0;
+    if (!raw || !dec || n_rows < 0 || out_size < 1 || out_size > OUT_LD) return fail("mlb_decode: bad argument");
+    if (decode_kind == MLB_DECODE_LOCO && out_size < 9) return fail("mlb_decode: extract_outputs needs >= 9 columns");
+    if (decode_kind == MLB_DECODE_MONO && out_size < 9) return fail("mlb_decode: extract_outputs_mono needs 9 columns");
+    if (decode_kind == MLB_DECODE_DB && out_size < 2) return fail("mlb_decode: needs 2 columns");
+    decode_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw, n_rows, out_size, decode_kind, dec);
+    CU(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+extern "C" int mlb_laplace_std(const float* d_bi, int n_pass, int n_rows, int n_samples, uint64_t seed, float* out_std,
+                               void* stream) {
+    if (n_rows == 0) return 0;
+    if (!d_bi || !out_std || n_pass < 1 || n_rows < 0 || n_samples < 1) return fail("mlb_laplace_std: bad argument");
+    laplace_std_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_bi, n_pass, n_rows, n_samples, seed, out_std);
     CU(cudaGetLastError());
     g_launches++;
     return 0;

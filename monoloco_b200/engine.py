@@ -161,19 +161,37 @@ class LocoEngine:
             L_.check(self._lib.mlb_forward_host(self._h, C.byref(a), self._stream()), 'mlb_forward_host')
         return out
 
-    def stereo_filter(self, raw, dec, n_left, n_right):
-        """process.py:307-327 on device; returns (sel_raw, sel_dec, sel_idx) trimmed to the kept rows."""
+    def stereo_filter(self, raw, dec, n_left, n_right, xyzc=None):
+        """process.py:307-327 on device; returns (sel_raw, sel_dec, sel_idx[, sel_xyzc]) trimmed to the kept rows."""
         B = n_left * n_right
         sel_raw = torch.empty_like(raw)
         sel_dec = torch.empty_like(dec) if dec is not None else None
+        sel_xyzc = torch.empty_like(xyzc) if xyzc is not None else None
         sel_idx = torch.empty((B,), dtype=torch.int32, device=self.device)
         n_sel = torch.zeros((1,), dtype=torch.int32, device=self.device)
-        L_.check(self._lib.mlb_stereo_filter(raw.data_ptr(), dec.data_ptr() if dec is not None else None, n_left,
-                                             n_right, raw.shape[1], sel_raw.data_ptr(),
-                                             sel_dec.data_ptr() if dec is not None else None, sel_idx.data_ptr(),
+        ptr = lambda t_: t_.data_ptr() if t_ is not None else None  # noqa: E731
+        L_.check(self._lib.mlb_stereo_filter(raw.data_ptr(), ptr(dec), ptr(xyzc), n_left, n_right, raw.shape[1],
+                                             sel_raw.data_ptr(), ptr(sel_dec), ptr(sel_xyzc), sel_idx.data_ptr(),
                                              n_sel.data_ptr(), self._stream()), 'mlb_stereo_filter')
         n = int(n_sel.item())
-        return sel_raw[:n], (sel_dec[:n] if dec is not None else None), sel_idx[:n]
+        res = (sel_raw[:n], (sel_dec[:n] if dec is not None else None), sel_idx[:n])
+        return res + (sel_xyzc[:n],) if xyzc is not None else res
+
+    def epistemic_std(self, x, n_dropout, n_samples=100, seed=1, kind=L_.IN_X, kk=None):
+        """net.py:135-161: n_dropout stochastic forwards (top-level dropout on) -> (d, bi) -> Laplace sampling -> std.
+        Returns a CUDA tensor [B]."""
+        B = x.shape[0]
+        d_bi = torch.empty((n_dropout, B, 2), dtype=torch.float32, device=self.device)
+        c0 = 0 if self.output_size == 2 else 2  # net.py:146-149: db = outputs[:, 0:2] (monoloco) | outputs[:, 2:4]
+        for n in range(n_dropout):
+            out = self.forward(x, kk=kk, kind=kind, dropout=True, drop_seed=seed * 1000003 + n)
+            d_bi[n, :, 0] = out['raw'][:, c0]
+            d_bi[n, :, 1] = out['dec'][:, 4]  # bi = exp(s) * d, decoded in-kernel (process.py:132)
+        std = torch.empty((B,), dtype=torch.float32, device=self.device)
+        if B:
+            L_.check(self._lib.mlb_laplace_std(d_bi.data_ptr(), n_dropout, B, n_samples, int(seed), std.data_ptr(),
+                                               self._stream()), 'mlb_laplace_std')
+        return std
 
 
 def preprocess_device(kps, kk, zero_center=False):
@@ -188,6 +206,36 @@ def preprocess_device(kps, kk, zero_center=False):
         L_.check(lib.mlb_preprocess(kps.data_ptr(), B, kinv, 10.0, int(zero_center), out.data_ptr(),
                                     C.c_void_p(torch.cuda.current_stream(kps.device).cuda_stream)), 'mlb_preprocess')
     return out
+
+
+def dec_to_dict(raw, dec, stereo=None):
+    """[B,out] raw + [B,8] decoded (CUDA or CPU tensors) -> the reference's dic_out of CPU tensors
+    (process.py:231-278): h, w, l, ori, bi, xyzd, d, yaw=(alpha, ry)[, aux]."""
+    raw, dec = raw.detach().cpu(), dec.detach().cpu()
+    stereo = raw.shape[1] == 10 if stereo is None else stereo
+    dic = {'h': raw[:, 4:5], 'w': raw[:, 5:6], 'l': raw[:, 6:7], 'ori': raw[:, 7:9], 'bi': dec[:, 4:5],
+           'xyzd': dec[:, 0:4], 'd': dec[:, 3:4], 'yaw': (dec[:, 5:6], dec[:, 6:7])}
+    if stereo:
+        dic['aux'] = dec[:, 7:8]
+    return dic
+
+
+def decode_device(outputs, decode_kind=L_.DECODE_LOCO):
+    """extract_outputs(outputs) for a raw [m,9|10] tensor: decode kernel, then the dictionary of CPU tensors."""
+    lib = L_.lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError("monoloco_b200: no CUDA device -- the hot path has no CPU fallback")
+    raw = outputs.detach()
+    raw = (raw if raw.is_cuda else raw.cuda()).float().contiguous()
+    dec = torch.empty((raw.shape[0], 8), dtype=torch.float32, device=raw.device)
+    if raw.shape[0]:
+        L_.check(lib.mlb_decode(raw.data_ptr(), raw.shape[0], raw.shape[1], decode_kind, dec.data_ptr(),
+                                C.c_void_p(torch.cuda.current_stream(raw.device).cuda_stream)), 'mlb_decode')
+    if decode_kind == L_.DECODE_MONO:
+        r, d = raw.cpu(), dec.cpu()
+        return {'xyz': r[:, 0:3], 'zb': r[:, 2:4], 'h': r[:, 4:5], 'w': r[:, 5:6], 'l': r[:, 6:7], 'ori': r[:, 7:9],
+                'xyzd': d[:, 0:4], 'd': d[:, 3:4], 'bi': d[:, 4:5], 'yaw': (d[:, 5:6], d[:, 6:7])}
+    return dec_to_dict(raw, dec)
 
 
 def probe_ffma_tflops(device_index=0, iters=4096, reps=5, packed=False):

@@ -1,0 +1,191 @@
+"""
+`Loco` -- the drop-in for monoloco/network/net.py:23-133 (same constructor, `forward`, `post_process`,
+attributes), running pre-process + network + decode as one fused CUDA kernel per image.
+
+Differences that are deliberate and documented:
+  * the result tensors are produced on the GPU and returned as CPU float32 tensors, exactly the dict layout
+    callers index (`dic_out['xyzd'][:, 0:3]`, `dic_out['yaw'][0][idx]`, ...), plus one extra key `xyz_c` =
+    xyz_from_distance(d, bbox-centre ray) that `post_process` reuses;
+  * MC-dropout epistemic std uses an in-kernel counter RNG + inverse-CDF Laplace sampling instead of torch's
+    reseeded generator (equal in distribution, not sample-for-sample);
+  * there is no CPU mode: `device=None` selects the current CUDA device.
+"""
+import math
+from collections import defaultdict
+
+import torch
+
+from .. import _lib as L_
+from ..engine import dec_to_dict
+from ..utils import get_iou_matches, reorder_matches, get_keypoints, pixel_to_camera, xyz_from_distance
+from .architectures import MonolocoModel, LocoModel
+
+
+class Loco:
+    """Class for both MonoLoco and MonStereo (net.py:23-81)."""
+    LINEAR_SIZE_MONO = 256
+    N_SAMPLES = 100
+
+    def __init__(self, model, mode, net=None, device=None, n_dropout=0, p_dropout=0.2, linear_size=1024):
+        assert mode in ('mono', 'stereo'), "mode not recognized"
+        self.mode = mode
+        if net is None:
+            self.net = 'monoloco_pp' if mode == 'mono' else 'monstereo'
+        else:
+            # net.py:41-44 is unreachable in the reference (reads self.net before assignment); here the documented
+            # intent is implemented: legacy nets are mono-only
+            assert net in ('monstereo', 'monoloco', 'monoloco_p', 'monoloco_pp')
+            if net != 'monstereo':
+                assert mode == 'mono', "Assert arguments mode and net are in conflict"
+            self.net = net
+
+        if self.net == 'monstereo':
+            input_size, output_size = 68, 10
+        elif self.net == 'monoloco_p':
+            input_size, output_size, linear_size = 34, 9, 256
+        elif self.net == 'monoloco_pp':
+            input_size, output_size = 34, 9
+        else:
+            input_size, output_size = 34, 2
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("monoloco_b200.Loco needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device('cuda', torch.cuda.current_device()) if not device else torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("monoloco_b200.Loco runs on CUDA devices only")
+        self.n_dropout = n_dropout
+        self.epistemic = bool(self.n_dropout > 0)
+
+        if isinstance(model, str):
+            if self.net in ('monoloco', 'monoloco_p'):
+                self.model = MonolocoModel(p_dropout=p_dropout, input_size=input_size, linear_size=linear_size,
+                                           output_size=output_size)
+            else:
+                self.model = LocoModel(p_dropout=p_dropout, input_size=input_size, output_size=output_size,
+                                       linear_size=linear_size, device=self.device)
+            self.model.load_state_dict(torch.load(model, map_location=lambda storage, loc: storage))
+        else:
+            self.model = model
+        self.model.eval()
+        self.model.to(self.device)
+
+    # ------------------------------------------------------------------------------------------- forward
+    def forward(self, keypoints, kk, keypoints_r=None):
+        """net.py:83-133: keypoints [m][3][17] lists (+ right keypoints for stereo) -> dict of CPU tensors."""
+        if not keypoints:
+            return None
+        eng = self.model.engine()
+        with torch.no_grad():
+            kps = torch.tensor(keypoints, dtype=torch.float32).to(self.device)
+            if self.net == 'monstereo':
+                if keypoints_r:
+                    kps_r = torch.tensor(keypoints_r, dtype=torch.float32).to(self.device)
+                else:
+                    kps_r = kps[0:1, :].clone()  # net.py:115-116
+                out = eng.forward(kps, x_right=kps_r, kk=kk, kind=L_.IN_KPS_STEREO, want_xyzc=True)
+                raw, dec, _, xyzc = eng.stereo_filter(out['raw'], out['dec'], kps.shape[0], kps_r.shape[0],
+                                                      xyzc=out['xyzc'])  # process.py:307-327
+                dic_out = dec_to_dict(raw, dec, stereo=True)
+                dic_out['xyz_c'] = xyzc[:, 0:3].cpu()
+                n_out = kps.shape[0]  # net.py:130: outputs is the clustered 3-D tensor -> number of left poses
+                inputs = None
+            else:
+                zero_center = self.net == 'monoloco'
+                out = eng.forward(kps, kk=kk, kind=L_.IN_KPS, want_xyzc=True, want_x=self.epistemic,
+                                  zero_center=zero_center)
+                raw, dec = out['raw'], out['dec']
+                if self.net == 'monoloco':
+                    dic_out = {'d': raw[:, 0:1].cpu(), 'bi': dec[:, 4:5].cpu()}  # net.py:95-100
+                elif self.net == 'monoloco_p':
+                    r, d = raw.cpu(), dec.cpu()  # extract_outputs_mono, process.py:330-360
+                    dic_out = {'xyz': r[:, 0:3], 'zb': r[:, 2:4], 'h': r[:, 4:5], 'w': r[:, 5:6], 'l': r[:, 6:7],
+                               'ori': r[:, 7:9], 'xyzd': d[:, 0:4], 'd': d[:, 3:4], 'bi': d[:, 4:5],
+                               'yaw': (d[:, 5:6], d[:, 6:7])}
+                else:
+                    dic_out = dec_to_dict(raw, dec, stereo=False)
+                dic_out['xyz_c'] = out['xyzc'][:, 0:3].cpu()
+                n_out = raw.shape[0]
+                inputs = out.get('x')
+            if self.n_dropout > 0 and self.net != 'monstereo':
+                dic_out['epi'] = self.epistemic_uncertainty(inputs)
+            else:
+                dic_out['epi'] = [0.] * n_out
+        return dic_out
+
+    def epistemic_uncertainty(self, inputs):
+        """net.py:135-161: n_dropout stochastic passes (top-level dropout on) + Laplace sampling -> std per instance."""
+        assert self.net in ('monoloco', 'monoloco_p', 'monoloco_pp'), "Not supported for MonStereo"
+        eng = self.model.engine()
+        return eng.epistemic_std(inputs, self.n_dropout, n_samples=self.N_SAMPLES, seed=1).cpu()
+
+    # ------------------------------------------------------------------------------------------- post-process
+    @staticmethod
+    def post_process(dic_in, boxes, keypoints, kk, dic_gt=None, iou_min=0.3, reorder=True, verbose=False):
+        """net.py:163-248: final per-instance dictionary for visualisation / KITTI txt (host-side list logic)."""
+        dic_out = defaultdict(list)
+        if dic_in is None:
+            return dic_out
+        if dic_gt:
+            boxes_gt = dic_gt['boxes']
+            dds_gt = [el[3] for el in dic_gt['ys']]
+            matches = get_iou_matches(boxes, boxes_gt, iou_min=iou_min)
+            dic_out['gt'] = [True]
+            if verbose:
+                print("found {} matches with ground-truth".format(len(matches)))
+            idxs_matches = [el[0] for el in matches]
+            not_matches = [idx for idx, _ in enumerate(boxes) if idx not in idxs_matches]
+        else:
+            matches = []
+            not_matches = list(range(len(boxes)))
+            if verbose:
+                print("NO ground-truth associated")
+        if reorder and matches:
+            matches = reorder_matches(matches, boxes, mode='left_right')
+        all_idxs = [idx for idx, _ in matches] + not_matches
+        dic_out['gt'] = [True] * len(matches) + [False] * len(not_matches)
+
+        uv_shoulders = get_keypoints(keypoints, mode='shoulder').tolist()
+        uv_heads = get_keypoints(keypoints, mode='head').tolist()
+        uv_centers_t = get_keypoints(keypoints, mode='center')
+        uv_centers = uv_centers_t.tolist()
+        xy_centers = pixel_to_camera(uv_centers_t, kk, 1)
+        xyz_c = dic_in.get('xyz_c') if isinstance(dic_in, dict) else None  # computed by the fused kernel
+
+        for idx in all_idxs:
+            box = boxes[idx]
+            dd_pred = float(dic_in['d'][idx])
+            bi = float(dic_in['bi'][idx])
+            var_y = float(dic_in['epi'][idx])
+            if xyz_c is not None and len(xyz_c) == len(boxes):
+                xyz_pred = xyz_c[idx]
+            else:
+                xyz_pred = xyz_from_distance(dd_pred, xy_centers[idx])[0]
+            distance = math.sqrt(float(xyz_pred[0]) ** 2 + float(xyz_pred[1]) ** 2 + float(xyz_pred[2]) ** 2)
+            conf = 0.035 * (box[-1]) / (bi / distance)
+            dic_out['boxes'].append(box)
+            dic_out['confs'].append(conf)
+            dic_out['dds_pred'].append(dd_pred)
+            dic_out['stds_ale'].append(bi)
+            dic_out['stds_epi'].append(var_y)
+            dic_out['xyz_pred'].append(xyz_pred.squeeze().tolist())
+            dic_out['uv_kps'].append(keypoints[idx])
+            dic_out['uv_centers'].append([round(uv_centers[idx][0]), round(uv_centers[idx][1])])
+            dic_out['uv_shoulders'].append([round(uv_shoulders[idx][0]), round(uv_shoulders[idx][1])])
+            dic_out['uv_heads'].append([round(uv_heads[idx][0]), round(uv_heads[idx][1])])
+            try:
+                dic_out['angles'].append(float(dic_in['yaw'][0][idx]))
+                dic_out['angles_egocentric'].append(float(dic_in['yaw'][1][idx]))
+            except KeyError:
+                continue
+            try:
+                dic_out['aux'].append(float(dic_in['aux'][idx]))
+            except KeyError:
+                continue
+
+        for idx, idx_gt in matches:
+            dd_real = dds_gt[idx_gt]
+            xyz_real = xyz_from_distance(dd_real, xy_centers[idx])
+            dic_out['dds_real'].append(dd_real)
+            dic_out['boxes_gt'].append(boxes_gt[idx_gt])
+            dic_out['xyz_real'].append(xyz_real.squeeze().tolist())
+        return dic_out

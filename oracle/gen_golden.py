@@ -233,6 +233,43 @@ def ref_epistemic():
                         bi=unnormalize_bi(torch.tensor([[10.0, -1.0], [25.0, 0.2]])).numpy())
 
 
+def ref_api():
+    """Host-side API fixtures: checkpoint ABI (state_dict keys/shapes), preprocess_pifpaf, load_calibration,
+    Loco.post_process with a synthetic ground truth."""
+    from monoloco.network.process import load_calibration
+    abi = {}
+    for name, m in (('loco_34_9_1024', LocoModel(34, 9, 1024, device='cpu')),
+                    ('loco_68_10_1024', LocoModel(68, 10, 1024, device='cpu')),
+                    ('loco_34_9_256_s2', LocoModel(34, 9, 256, num_stage=2, device='cpu')),
+                    ('monoloco_34_2_256', MonolocoModel(34, 2, 256)),
+                    ('monoloco_34_9_1024', MonolocoModel(34, 9, 1024))):
+        abi[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    ann = json.load(open(os.path.join(REF, 'tests', '002282.png.pifpaf.json')))
+    with open(os.path.join(OUT, 'pifpaf_002282.json'), 'w') as f:  # data fixture: 16 pifpaf detections
+        json.dump(ann, f)
+    boxes, keypoints = preprocess_pifpaf(ann, im_size=(1238, 374))
+    boxes2, _ = preprocess_pifpaf(json.load(open(os.path.join(REF, 'tests', '002282.png.pifpaf.json'))),
+                                  im_size=None, enlarge_boxes=False, min_conf=0.3)
+    calib = {'kitti_1238x374': load_calibration('kitti', (1238, 374)),
+             'nuscenes_800x450': load_calibration('nuscenes', (800, 450)),
+             'custom_1920x1080': load_calibration('custom', (1920, 1080), focal_length=5.7)}
+    kk = synthetic.KITTI_K
+    model, sd = build('loco', 34, 9, 1024, 3, 1)
+    net = Loco(model=model, mode='mono', device=torch.device('cpu'))
+    dic = net.forward(keypoints, kk)
+    # synthetic ground truth: shifted copies of 5 detections (matched) + 1 far-away box (unmatched)
+    boxes_gt = [[b[0] + 3, b[1] - 2, b[2] + 3, b[3] - 2] for b in boxes[2:7]] + [[5., 5., 20., 40.]]
+    ys = [[0, 0, 0, 10.0 + 3 * i, 0, 0, 0, 0, 0, 0] for i in range(len(boxes_gt))]
+    dic_gt = {'boxes': boxes_gt, 'ys': ys}
+    post = Loco.post_process(dic, boxes, keypoints, kk, dic_gt=dic_gt)
+    post_nogt = Loco.post_process(dic, boxes, keypoints, kk, dic_gt=None)
+    out = {'abi': abi, 'boxes': boxes, 'keypoints': keypoints, 'boxes_noenlarge_conf03': boxes2, 'calib': calib,
+           'dic_gt': dic_gt, 'post': {k: v for k, v in post.items()}, 'post_nogt': {k: v for k, v in post_nogt.items()}}
+    with open(os.path.join(OUT, 'ref_api.json'), 'w') as f:
+        json.dump(out, f)
+    print('api', len(boxes), len(boxes2), sorted(post.keys()))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     kat_preprocess()
@@ -240,4 +277,5 @@ if __name__ == '__main__':
     ref_loco_forward()
     ref_losses()
     ref_epistemic()
+    ref_api()
     print('done')
