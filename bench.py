@@ -34,6 +34,16 @@ METRIC = "detections/sec LocoModel(34->9, 3x1024) fused forward @ batch 4096 per
 UNIT = "detections/s"
 
 
+def measured_traffic():
+    """dram__bytes_read+write of the forward kernel from the committed ncu capture (profiles/forward_traffic.json)."""
+    path = os.path.join(ROOT, 'profiles', 'forward_traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get('traffic_bytes'), d.get('source')
+    return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -152,6 +162,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--rows-per-group', type=int, default=0)
+    ap.add_argument('--gather', default='fused', choices=['fused', 'nccl'],
+                    help='multi-GPU output all-gather: fused peer stores from the kernel epilogue, or NCCL')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -179,15 +191,16 @@ def main():
     kps_host = torch.from_numpy(synthetic.make_keypoints(B, seed=rank)).pin_memory()
     kps = kps_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = torch.empty((world * B, 17), dtype=torch.float32, device=dev) if world > 1 else None
     st = torch.cuda.current_stream(dev)
+    sharded = None
+    if world > 1:
+        from monoloco_b200 import distributed as D
+        sharded = D.ShardedLoco(eng, world * B, mode=args.gather)
 
     def step():
-        out = eng.forward(kps, kk=kk, kind=L_.IN_KPS, rows_per_group=args.rows_per_group)
-        if world > 1:
-            local = torch.cat((out['raw'], out['dec']), dim=1)
-            dist.all_gather_into_tensor(gathered, local)
-        return out
+        if sharded is not None:
+            return sharded.forward(kps, kk, rows_per_group=args.rows_per_group)  # forward + all-gather of [N*B, 20] rows
+        return eng.forward(kps, kk=kk, kind=L_.IN_KPS, rows_per_group=args.rows_per_group)
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -255,13 +268,16 @@ def main():
                                    "forward + decode, batch %d per GPU" % B,
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
                        "l2": "flushed before every timed step (256 MiB memset)",
-                       "collective": "all_gather_into_tensor [B,17] fp32 per step" if world > 1 else "none"},
+                       "collective": ("none" if world == 1 else
+                                      ("kernel-epilogue peer stores over NVLink (cudaIpc) + barrier" if args.gather == 'fused'
+                                       else "NCCL all_gather_into_tensor") + " of [N*B,20] fp32 rows per step")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 51 * 4, "d2h_bytes_per_step": B * 17 * 4,
                     "ms_per_step": e2e_ms},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved_gbs / hbm_peak, "traffic": measured_traffic()[0] if B == 4096 else None,
+                         "traffic_source": measured_traffic()[1], "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes,
                          "note": "at batch 4096 the path is FP32-FFMA bound (SURVEY.md §0.4); see fp32",
                          "fp32": {"achieved": achieved_tf, "peak": ffma_peak, "unit": "TFLOP/s",

@@ -22,6 +22,9 @@ extern "C" {
 
 #define MLB_ABI_VERSION 1
 #define MLB_MAX_OPS 32
+#define MLB_MAX_PEERS 8
+#define MLB_GATHER_LD 20   /* floats per gathered row: raw at [0,out), dec at [12,20) */
+#define MLB_GATHER_DEC 12
 
 /* ---- layer program: one entry per Linear(+BN+ReLU+Dropout)(+residual) of architectures.py ---- */
 enum { MLB_OP_GEMM = 0, /* L-wide Linear, weights streamed through the TMA ring                    */
@@ -102,6 +105,13 @@ typedef struct mlb_forward_args {
     float* out_x;           /* [B, input_size] the pre-processed network input, or NULL             */
     const uint8_t* drop_mask; /* [sites][B][L] keep-mask (1 keep) for MLB_FWD_DROPOUT, or NULL      */
     uint64_t drop_seed;     /* in-kernel counter RNG seed when drop_mask == NULL                    */
+    /* fused all-gather (multi-GPU, one process per GPU): the decode epilogue additionally stores every row as
+     * [raw(out) | pad | dec(8)] (MLB_GATHER_LD floats, dec at MLB_GATHER_DEC) into n_gather buffers -- this
+     * rank's and its NVLink peers' (pointers from mlb_ipc_open) -- at row gather_row0 + i.                  */
+    float* gather[MLB_MAX_PEERS];
+    int32_t n_gather;       /* 0 = off                                                              */
+    int32_t reserved0;
+    int64_t gather_row0;    /* first global row of this rank's shard                                */
 } mlb_forward_args;
 
 /* Fused pre-process -> MLP -> heads -> decode on DEVICE buffers (replaces net.py:92-124 body:
@@ -133,6 +143,15 @@ int mlb_decode(const float* raw, int n_rows, int out_size, int decode_kind, floa
  * (counter RNG, `seed`) and writes the unbiased std over all n_pass*n_samples draws to out_std [n_rows]. */
 int mlb_laplace_std(const float* d_bi, int n_pass, int n_rows, int n_samples, uint64_t seed, float* out_std,
                     void* stream);
+
+/* ---- NVLink peer buffers for the fused all-gather (cudaIpc*, one process per GPU) ---- */
+#define MLB_IPC_HANDLE_BYTES 64
+/* cudaMalloc `bytes` on `device` (zero-filled) and export an IPC handle for the other ranks. */
+int mlb_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char handle[MLB_IPC_HANDLE_BYTES]);
+/* map a peer rank's buffer into this process (cudaIpcOpenMemHandle, peer access over NVLink). */
+int mlb_ipc_open(int device, const unsigned char handle[MLB_IPC_HANDLE_BYTES], void** dev_ptr);
+int mlb_ipc_close(void* dev_ptr);
+int mlb_ipc_free(void* dev_ptr);
 
 /* FP32-FFMA throughput probe (roofline denominator for the fp32-bound regime): every thread of
  * `blocks` x 512 threads runs |iters| x 128 FMAs in 16 independent chains (iters < 0: packed fma.rn.f32x2).

@@ -7,6 +7,10 @@ from .build import LIB_PATH
 
 MLB_ABI_VERSION = 1
 MLB_MAX_OPS = 32
+MLB_MAX_PEERS = 8
+GATHER_LD = 20
+GATHER_DEC = 12
+IPC_HANDLE_BYTES = 64
 OP_GEMM, OP_HEAD = 0, 1
 F_RELU, F_SAVE_RES, F_ADD_RES, F_DROPOUT, F_IN_XIN = 1, 2, 4, 8, 16
 DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
@@ -14,7 +18,7 @@ IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM = 1, 2, 4
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
-           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_probe_ffma',
+           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_probe_ffma',
            'mlb_launch_count']
 
 
@@ -33,7 +37,9 @@ class MlbForwardArgs(C.Structure):
     _fields_ = [('input_kind', C.c_int32), ('flags', C.c_int32), ('n_rows', C.c_int32), ('n_left', C.c_int32),
                 ('n_right', C.c_int32), ('rows_per_group', C.c_int32), ('kinv', C.c_float * 9), ('z_met', C.c_float),
                 ('x', C.c_void_p), ('x_right', C.c_void_p), ('out_raw', C.c_void_p), ('out_dec', C.c_void_p),
-                ('out_xyzc', C.c_void_p), ('out_x', C.c_void_p), ('drop_mask', C.c_void_p), ('drop_seed', C.c_uint64)]
+                ('out_xyzc', C.c_void_p), ('out_x', C.c_void_p), ('drop_mask', C.c_void_p), ('drop_seed', C.c_uint64),
+                ('gather', C.c_void_p * MLB_MAX_PEERS), ('n_gather', C.c_int32), ('reserved0', C.c_int32),
+                ('gather_row0', C.c_int64)]
 
 
 _lib = None
@@ -62,6 +68,10 @@ def lib():
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.mlb_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.mlb_laplace_std.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    l.mlb_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    l.mlb_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    l.mlb_ipc_close.argtypes = [C.c_void_p]
+    l.mlb_ipc_free.argtypes = [C.c_void_p]
     l.mlb_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     l.mlb_launch_count.restype = C.c_uint64
     if l.mlb_abi_version() != MLB_ABI_VERSION:

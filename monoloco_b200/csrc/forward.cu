@@ -52,6 +52,9 @@ struct FwdParams {
     float p_drop;
     float* res_scratch;
     int* err_flag;
+    float* gather[MLB_MAX_PEERS];
+    int n_gather;
+    long long gather_row0;
 };
 
 // Laplace / spherical / orientation decode of one raw output row (process.py:231-278, 330-360; net.py:95-100).
@@ -431,6 +434,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                         dst[0] = make_float4(x, y, z, d);
                         dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
                     }
+                    // fused all-gather: the same row goes straight into every rank's gather buffer over NVLink
+                    for (int pg = 0; pg < p.n_gather; ++pg) {
+                        float* dst = p.gather[pg] + (size_t)(p.gather_row0 + (long long)grow) * MLB_GATHER_LD;
+                        for (int k = 0; k < p.out_size; ++k) dst[k] = o[k];
+                        reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
+                        reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
+                    }
                     if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
                         // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
                         const float uc = cen[sr * 4 + 0], vc = cen[sr * 4 + 1];
@@ -806,6 +816,13 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     p.p_drop = d.p_dropout;
     p.res_scratch = h->res_scratch;
     p.err_flag = h->err_flag_dev;
+    if (a->n_gather < 0 || a->n_gather > MLB_MAX_PEERS) return fail("mlb_forward: n_gather out of range");
+    p.n_gather = a->n_gather;
+    p.gather_row0 = a->gather_row0;
+    for (int i = 0; i < a->n_gather; ++i) {
+        if (!a->gather[i]) return fail("mlb_forward: null gather pointer");
+        p.gather[i] = a->gather[i];
+    }
 
     // consumer warpgroups (one active warp per 128 hidden columns) + one producer warpgroup (setmaxnreg split)
     const int threads = ((d.linear_size / 128 + 3) / 4) * 128 + 128;
@@ -880,6 +897,7 @@ extern "C" int mlb_forward_host(mlb_handle h, const mlb_forward_args* a, void* s
     dev.out_xyzc = a->out_xyzc ? h->st_xyzc : nullptr;
     dev.out_x = a->out_x ? h->st_x : nullptr;
     dev.drop_mask = nullptr;
+    dev.n_gather = 0;
     if (a->drop_mask) return fail("mlb_forward_host: drop_mask is a device-only option");
     if (mlb_forward(h, &dev, stream)) return -1;
     CU(cudaMemcpyAsync(a->out_raw, h->st_raw, B * d.output_size * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -940,6 +958,42 @@ extern "C" int mlb_laplace_std(const float* d_bi, int n_pass, int n_rows, int n_
     laplace_std_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_bi, n_pass, n_rows, n_samples, seed, out_std);
     CU(cudaGetLastError());
     g_launches++;
+    return 0;
+}
+
+extern "C" int mlb_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char handle[MLB_IPC_HANDLE_BYTES]) {
+    if (!dev_ptr || !handle || bytes == 0) return fail("mlb_ipc_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= MLB_IPC_HANDLE_BYTES, "handle size");
+    CU(cudaSetDevice(device));
+    void* ptr = nullptr;
+    CU(cudaMalloc(&ptr, bytes));
+    CU(cudaMemset(ptr, 0, bytes));
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, ptr));
+    memset(handle, 0, MLB_IPC_HANDLE_BYTES);
+    memcpy(handle, &hd, sizeof(hd));
+    *dev_ptr = ptr;
+    return 0;
+}
+
+extern "C" int mlb_ipc_open(int device, const unsigned char handle[MLB_IPC_HANDLE_BYTES], void** dev_ptr) {
+    if (!dev_ptr || !handle) return fail("mlb_ipc_open: bad argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, sizeof(hd));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = ptr;
+    return 0;
+}
+
+extern "C" int mlb_ipc_close(void* dev_ptr) {
+    if (dev_ptr) CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+extern "C" int mlb_ipc_free(void* dev_ptr) {
+    if (dev_ptr) CU(cudaFree(dev_ptr));
     return 0;
 }
 

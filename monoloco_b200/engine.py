@@ -80,7 +80,8 @@ class LocoEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def forward(self, x, x_right=None, kk=None, kind=L_.IN_X, want_dec=True, want_xyzc=False, want_x=False,
-                zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=False):
+                zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=False,
+                gather_ptrs=None, gather_row0=0):
         """x: float32 CUDA tensor ([B,in] | [B,3,17] | left [L,3,17]).  Returns dict of CUDA tensors."""
         assert x.is_cuda and x.dtype == torch.float32
         x = x.contiguous()
@@ -120,6 +121,11 @@ class LocoEngine:
             drop_mask = drop_mask.contiguous()
             a.drop_mask = drop_mask.data_ptr()
         a.drop_seed = int(drop_seed)
+        if gather_ptrs:
+            a.n_gather = len(gather_ptrs)
+            for i, ptr in enumerate(gather_ptrs):
+                a.gather[i] = ptr
+            a.gather_row0 = int(gather_row0)
         if B > 0:
             L_.check(self._lib.mlb_forward(self._h, C.byref(a), self._stream()), 'mlb_forward')
         return out
