@@ -111,6 +111,7 @@ class ShardedLoco:
         self.n_total = n_total_rows
         self.start, self.stop = shard_range(n_total_rows, self.world, self.rank)
         self.buf = PeerGatherBuffer(n_total_rows, engine.index, group) if mode == 'fused' else None
+        self._flag = torch.zeros(1, dtype=torch.float32, device=engine.device)
 
     def forward(self, kps_local, kk, rows_per_group=0):
         """kps_local: this rank's [stop-start, 3, 17] CUDA keypoints.  Returns the gathered [n_total, GATHER_LD] rows."""
@@ -118,8 +119,9 @@ class ShardedLoco:
         if self.mode == 'fused':
             self.eng.forward(kps_local, kk=kk, kind=L_.IN_KPS, rows_per_group=rows_per_group,
                              gather_ptrs=self.buf.ptrs, gather_row0=self.start)
-            torch.cuda.current_stream().synchronize()  # peer stores are complete when the kernel has retired
-            dist.barrier(group=self.group)
+            # peer stores are complete when the kernel has retired; a 1-element all-reduce enqueued behind it on the
+            # stream is the cross-rank barrier (no host synchronisation)
+            dist.all_reduce(self._flag, group=self.group)
             return self.buf.tensor()
         out = self.eng.forward(kps_local, kk=kk, kind=L_.IN_KPS, rows_per_group=rows_per_group)
         return all_gather_rows(pack_rows(out['raw'], out['dec']), self.n_total, self.group)
