@@ -144,6 +144,62 @@ int mlb_decode(const float* raw, int n_rows, int out_size, int decode_kind, floa
 int mlb_laplace_std(const float* d_bi, int n_pass, int n_rows, int n_samples, uint64_t seed, float* out_std,
                     void* stream);
 
+/* ---- training step (trainer.py:153-161: model(inputs) in train mode, mt_loss, loss.backward()) -------------
+ * One persistent cooperative kernel per direction: forward (train-mode BatchNorm1d = batch statistics with a
+ * grid-wide reduction per layer, Dropout with a counter RNG or explicit masks, running-stat update) and backward
+ * (dL/dout -> every parameter gradient); mlb_train_step fuses forward + MultiTaskLoss + backward in ONE launch.
+ * All pointers are device pointers to fp32 tensors in the reference's native layouts (nn.Linear.weight [out,in]).
+ * LocoModel topology only (architectures.py:48-71), which is what Trainer builds (trainer.py:115-122). */
+#define MLB_MAX_BLOCKS 16
+enum { MLB_TASK_D = 0, MLB_TASK_X = 1, MLB_TASK_Y = 2, MLB_TASK_H = 3, MLB_TASK_W = 4, MLB_TASK_L = 5,
+       MLB_TASK_ORI = 6, MLB_TASK_AUX = 7 };  /* trainer.py:40, losses.py:76-101 */
+
+typedef struct mlb_train_block {   /* one L-wide Linear (+BatchNorm1d+ReLU+Dropout) in forward order           */
+    int32_t K;                     /* in_features                                                              */
+    int32_t has_bn;                /* 0 only for LocoModel.w2 (architectures.py:59)                            */
+    int32_t res_src;               /* index of the block whose output is added to this one's (x + y), or -1   */
+    int32_t reserved;
+    const float* W;                /* [L, K]                                                                   */
+    const float* b;                /* [L]                                                                      */
+    const float* gamma;            /* BatchNorm1d.weight [L]                                                   */
+    const float* beta;             /* BatchNorm1d.bias   [L]                                                   */
+    float* running_mean;           /* updated in place with momentum (may be NULL)                             */
+    float* running_var;
+    float* dW;                     /* gradient outputs, overwritten: [L, K], [L], [L], [L]                     */
+    float* db;
+    float* dgamma;
+    float* dbeta;
+} mlb_train_block;
+
+typedef struct mlb_train_args {
+    int32_t n_rows, input_size, output_size, linear_size, n_blocks;
+    int32_t aux_block;             /* block whose output feeds w_aux (LocoModel.w2); w_fin reads the last block */
+    int32_t update_running_stats;  /* 1 in training (nn.BatchNorm1d momentum update, unbiased variance)         */
+    int32_t rows_per_group;        /* 0 = auto                                                                  */
+    float p_dropout, bn_eps, bn_momentum, reserved0;
+    uint64_t drop_seed;            /* counter-RNG seed (must be the same in forward and backward)               */
+    const uint8_t* drop_mask;      /* optional explicit keep masks [n_bn_blocks][B][L] (parity tests)           */
+    const float* x;                /* [B, input_size] pre-processed inputs                                      */
+    float* out;                    /* [B, output_size]                                                          */
+    const float* g_out;            /* backward only: dL/d(out) [B, output_size]                                 */
+    const float* W_aux; const float* b_aux; const float* W_fin; const float* b_fin;   /* [1,L],[1],[out-1,L],[out-1] */
+    float* dW_aux; float* db_aux; float* dW_fin; float* db_fin;
+    /* fused MultiTaskLoss / AutoTuneMultiTaskLoss (losses.py:28-73), mlb_train_step only */
+    const float* labels;           /* [B, label_ld]  Y = [theta, psi, z, r, h, w, l, sin, cos, yaw(, s_match)]   */
+    int32_t label_ld, n_tasks;
+    int32_t tasks[8];              /* MLB_TASK_*                                                                */
+    float task_scale[8];           /* lambda_t (MultiTaskLoss) or lambda_t / (2 exp(log_sigma_t)^2) (AutoTune)  */
+    float* loss_vals;              /* [8] unweighted per-task means (device)                                    */
+} mlb_train_args;
+
+typedef struct mlb_train* mlb_train_handle;
+/* workspace for up to max_rows detections: saved activations, pre-BN outputs, gradients, transposed weights. */
+int mlb_train_create(int device, int max_rows, int input_size, int linear_size, int n_blocks, mlb_train_handle* out);
+void mlb_train_destroy(mlb_train_handle h);
+int mlb_train_forward(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
+int mlb_train_backward(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
+int mlb_train_step(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
+
 /* ---- NVLink peer buffers for the fused all-gather (cudaIpc*, one process per GPU) ---- */
 #define MLB_IPC_HANDLE_BYTES 64
 /* cudaMalloc `bytes` on `device` (zero-filled) and export an IPC handle for the other ranks. */

@@ -18,7 +18,8 @@ IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM = 1, 2, 4
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
-           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_probe_ffma',
+           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
+           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_probe_ffma',
            'mlb_launch_count']
 
 
@@ -40,6 +41,30 @@ class MlbForwardArgs(C.Structure):
                 ('out_xyzc', C.c_void_p), ('out_x', C.c_void_p), ('drop_mask', C.c_void_p), ('drop_seed', C.c_uint64),
                 ('gather', C.c_void_p * MLB_MAX_PEERS), ('n_gather', C.c_int32), ('reserved0', C.c_int32),
                 ('gather_row0', C.c_int64)]
+
+
+MLB_MAX_BLOCKS = 16
+TASK_IDS = {'d': 0, 'x': 1, 'y': 2, 'h': 3, 'w': 4, 'l': 5, 'ori': 6, 'aux': 7}
+
+
+class MlbTrainBlock(C.Structure):
+    _fields_ = [('K', C.c_int32), ('has_bn', C.c_int32), ('res_src', C.c_int32), ('reserved', C.c_int32),
+                ('W', C.c_void_p), ('b', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p),
+                ('running_mean', C.c_void_p), ('running_var', C.c_void_p),
+                ('dW', C.c_void_p), ('db', C.c_void_p), ('dgamma', C.c_void_p), ('dbeta', C.c_void_p)]
+
+
+class MlbTrainArgs(C.Structure):
+    _fields_ = [('n_rows', C.c_int32), ('input_size', C.c_int32), ('output_size', C.c_int32), ('linear_size', C.c_int32),
+                ('n_blocks', C.c_int32), ('aux_block', C.c_int32), ('update_running_stats', C.c_int32),
+                ('rows_per_group', C.c_int32),
+                ('p_dropout', C.c_float), ('bn_eps', C.c_float), ('bn_momentum', C.c_float), ('reserved0', C.c_float),
+                ('drop_seed', C.c_uint64), ('drop_mask', C.c_void_p), ('x', C.c_void_p), ('out', C.c_void_p),
+                ('g_out', C.c_void_p),
+                ('W_aux', C.c_void_p), ('b_aux', C.c_void_p), ('W_fin', C.c_void_p), ('b_fin', C.c_void_p),
+                ('dW_aux', C.c_void_p), ('db_aux', C.c_void_p), ('dW_fin', C.c_void_p), ('db_fin', C.c_void_p),
+                ('labels', C.c_void_p), ('label_ld', C.c_int32), ('n_tasks', C.c_int32),
+                ('tasks', C.c_int32 * 8), ('task_scale', C.c_float * 8), ('loss_vals', C.c_void_p)]
 
 
 _lib = None
@@ -72,6 +97,11 @@ def lib():
     l.mlb_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     l.mlb_ipc_close.argtypes = [C.c_void_p]
     l.mlb_ipc_free.argtypes = [C.c_void_p]
+    l.mlb_train_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    l.mlb_train_destroy.argtypes = [C.c_void_p]
+    l.mlb_train_destroy.restype = None
+    for fn in (l.mlb_train_forward, l.mlb_train_backward, l.mlb_train_step):
+        fn.argtypes = [C.c_void_p, C.POINTER(MlbTrainArgs), C.POINTER(MlbTrainBlock), C.c_void_p]
     l.mlb_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     l.mlb_launch_count.restype = C.c_uint64
     if l.mlb_abi_version() != MLB_ABI_VERSION:

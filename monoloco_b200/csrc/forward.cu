@@ -658,8 +658,10 @@ struct mlb_model {
     bool attr_set;
 };
 
-static thread_local std::string g_err;
+thread_local std::string g_mlb_err;  // shared with train.cu
+#define g_err g_mlb_err
 static std::atomic<uint64_t> g_launches{0};
+void mlb_count_launch() { g_launches++; }
 
 static int fail(const std::string& msg) {
     g_err = msg;

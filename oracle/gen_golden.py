@@ -188,7 +188,7 @@ def ref_losses():
     for mode, isz, osz, seed in (('mono', 34, 9, 21), ('stereo', 68, 10, 22)):
         tasks = ('d', 'x', 'y', 'h', 'w', 'l', 'ori') + (('aux',) if mode == 'stereo' else ())
         lambdas = (1,) * len(tasks)
-        L, st, B = 64, 2, 48
+        L, st, B = 128, 2, 48
         sd = synthetic.make_state_dict('loco', isz, osz, L, st, seed)
         model = LocoModel(isz, osz, L, 0.0, st, device='cpu')
         model.load_state_dict(sd_to_torch(sd))

@@ -28,31 +28,35 @@ def _bn(x, sd, name, training, momentum=0.1):
                         sd[name + '.bias'], training=training, momentum=momentum, eps=1e-5)
 
 
-def _block(x, sd, lin, bn, training, p, relu=True):
+def _block(x, sd, lin, bn, training, p, relu=True, masks=None):
     y = F.linear(x, sd[lin + '.weight'], sd[lin + '.bias'])
     if bn is not None:
         y = _bn(y, sd, bn, training)
     if relu:
         y = F.relu(y)
     if training and p > 0:
-        y = F.dropout(y, p, True)
+        if masks is not None:  # explicit keep masks (one per BatchNorm block, forward order): nn.Dropout semantics
+            y = y * masks.pop(0).to(y.dtype) / (1.0 - p)
+        else:
+            y = F.dropout(y, p, True)
     return y
 
 
-def model_forward(sd, x, training=False, p_dropout=0.0):
+def model_forward(sd, x, training=False, p_dropout=0.0, masks=None):
     """LocoModel (architectures.py:48-71) or MonolocoModel (:135-145), picked from the checkpoint keys."""
-    y = _block(x, sd, 'w1', 'batch_norm1', training, p_dropout)
+    masks = list(masks) if masks is not None else None
+    y = _block(x, sd, 'w1', 'batch_norm1', training, p_dropout, masks=masks)
     i = 0
     while 'linear_stages.%d.w1.weight' % i in sd:
         p = 'linear_stages.%d' % i
-        z = _block(y, sd, p + '.w1', p + '.batch_norm1', training, p_dropout)
-        z = _block(z, sd, p + '.w2', p + '.batch_norm2', training, p_dropout)
+        z = _block(y, sd, p + '.w1', p + '.batch_norm1', training, p_dropout, masks=masks)
+        z = _block(z, sd, p + '.w2', p + '.batch_norm2', training, p_dropout, masks=masks)
         y = y + z
         i += 1
     if 'w_fin.weight' in sd:
         y = F.linear(y, sd['w2.weight'], sd['w2.bias'])
         aux = F.linear(y, sd['w_aux.weight'], sd['w_aux.bias'])
-        y = _block(y, sd, 'w3', 'batch_norm3', training, p_dropout)
+        y = _block(y, sd, 'w3', 'batch_norm3', training, p_dropout, masks=masks)
         y = F.linear(y, sd['w_fin.weight'], sd['w_fin.bias'])
         return torch.cat((y, aux), dim=1)
     return F.linear(y, sd['w2.weight'], sd['w2.bias'])

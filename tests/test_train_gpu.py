@@ -1,0 +1,173 @@
+"""GPU: the fused training step (forward + multi-task Laplace loss + backward) against the live-reference fixtures
+(tests/golden/ref_train_*.npz: loss, per-task values, every parameter gradient, running-stat update) and against the
+torch-autograd oracle (oracle/torch_port.py) at larger sizes with explicit dropout masks.
+Gradient rule: |a-b| <= 1e-4*|b| + 2e-5*max|b| per tensor and relative L2 <= 2e-5."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _model(isz, osz, L, st, seed, p_dropout=0.0):
+    from monoloco_b200 import synthetic
+    from monoloco_b200.network.architectures import LocoModel
+    sd = synthetic.make_state_dict('loco', isz, osz, L, st, seed)
+    m = LocoModel(isz, osz, L, p_dropout=p_dropout, num_stage=st)
+    m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+    return m.cuda(), sd
+
+
+def _cmp_grad(name, got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, name
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    err = np.abs(got - ref)
+    assert (err <= 1e-4 * np.abs(ref) + 2e-5 * scale).all(), (name, float(err.max()), scale)
+    nrm = float(np.linalg.norm(ref))
+    if nrm > 1e-6:
+        assert float(np.linalg.norm(got - ref)) / nrm <= 2e-5, (name, float(np.linalg.norm(got - ref)) / nrm)
+
+
+TASKS = {'mono': ('d', 'x', 'y', 'h', 'w', 'l', 'ori'), 'stereo': ('d', 'x', 'y', 'h', 'w', 'l', 'ori', 'aux')}
+
+
+@pytest.mark.parametrize('mode', ['mono', 'stereo'])
+@pytest.mark.parametrize('auto', [False, True])
+def test_train_dropin_vs_reference(mode, auto):
+    """trainer.py:153-158 verbatim: outputs = model(inputs); loss, _ = mt_loss(outputs, labels); loss.backward()."""
+    from monoloco_b200.train import CompositeLoss, MultiTaskLoss, AutoTuneMultiTaskLoss
+    f = np.load(os.path.join(GOLDEN, 'ref_train_%s_%s.npz' % (mode, 'auto' if auto else 'mtl')))
+    isz, osz, L, st, seed, B = [int(v) for v in f['cfg']]
+    model, _ = _model(isz, osz, L, st, seed)
+    tasks = TASKS[mode]
+    losses_tr, losses_val = CompositeLoss(tasks)()
+    if auto:
+        mt = AutoTuneMultiTaskLoss(losses_tr, losses_val, (1,) * len(tasks), tasks).cuda()
+        with torch.no_grad():
+            mt.log_sigmas.copy_(torch.from_numpy(f['log_sigmas']))
+    else:
+        mt = MultiTaskLoss(losses_tr, losses_val, (1,) * len(tasks), tasks)
+    model.train()
+    x, y = torch.from_numpy(f['x']).cuda(), torch.from_numpy(f['y']).cuda()
+    out = model(x)
+    assert np.allclose(out.detach().cpu().numpy(), f['out'], rtol=1e-5, atol=1e-5)
+    loss, vals = mt(out, y, phase='train')
+    assert abs(float(loss) - float(f['loss'])) <= 3e-6 * abs(float(f['loss']))
+    assert np.allclose(np.array([float(v) for v in vals]), f['vals'], rtol=1e-5)
+    loss.backward()
+    for n, p in model.named_parameters():
+        _cmp_grad(n, p.grad.cpu().numpy(), f['grad.' + n])
+    for n, b in model.named_buffers():
+        if 'num_batches' in n:
+            assert int(b) == int(f['buf.' + n])
+        else:
+            assert np.allclose(b.cpu().numpy(), f['buf.' + n], rtol=1e-5, atol=1e-6), n
+    if auto:
+        assert np.allclose(mt.log_sigmas.grad.cpu().numpy(), f['grad.log_sigmas'], rtol=1e-5)
+    with torch.no_grad():
+        _, vals_val = mt(out.detach(), y, phase='val')
+    assert np.allclose(np.array([float(v) for v in vals_val]), f['vals_val'], rtol=2e-5)
+
+
+@pytest.mark.parametrize('mode', ['mono', 'stereo'])
+@pytest.mark.parametrize('auto', [False, True])
+def test_train_step_single_launch_vs_reference(mode, auto):
+    """forward + loss + backward in ONE cooperative launch."""
+    from monoloco_b200.train import train_step
+    from monoloco_b200 import _lib as L_
+    f = np.load(os.path.join(GOLDEN, 'ref_train_%s_%s.npz' % (mode, 'auto' if auto else 'mtl')))
+    isz, osz, L, st, seed, B = [int(v) for v in f['cfg']]
+    model, _ = _model(isz, osz, L, st, seed)
+    model.train()
+    ls = torch.nn.Parameter(torch.from_numpy(f['log_sigmas']).cuda()) if auto else None
+    n0 = L_.lib().mlb_launch_count()
+    loss, vals, out = train_step(model, torch.from_numpy(f['x']).cuda(), torch.from_numpy(f['y']).cuda(), TASKS[mode],
+                                 log_sigmas=ls)
+    assert L_.lib().mlb_launch_count() - n0 == 1
+    assert np.allclose(out.cpu().numpy(), f['out'], rtol=1e-5, atol=1e-5)
+    assert abs(float(loss) - float(f['loss'])) <= 3e-6 * abs(float(f['loss']))
+    assert np.allclose(np.array([float(v) for v in vals]), f['vals'], rtol=1e-5)
+    for n, p in model.named_parameters():
+        _cmp_grad(n, p.grad.cpu().numpy(), f['grad.' + n])
+    if auto:
+        assert np.allclose(ls.grad.cpu().numpy(), f['grad.log_sigmas'], rtol=1e-5)
+
+
+@pytest.mark.parametrize('L,st,B,p', [(256, 3, 301, 0.2), (1024, 3, 4096, 0.2), (1024, 1, 29, 0.0), (512, 3, 1000, 0.5)])
+def test_train_step_vs_torch_autograd(L, st, B, p):
+    """Full-size training step (BASELINE config 4: batch 4096) with explicit dropout keep-masks vs torch autograd."""
+    from oracle import torch_port as T
+    from monoloco_b200 import synthetic
+    from monoloco_b200.train import train_step
+    model, sd = _model(34, 9, L, st, 7, p_dropout=p)
+    model.train()
+    x = synthetic.make_inputs(B, 34, seed=3)
+    y = synthetic.make_labels(B, seed=4)
+    n_bn = 2 * st + 2
+    rng = np.random.RandomState(5)
+    masks = (rng.uniform(size=(n_bn, B, L)) >= p).astype(np.uint8)
+    tasks = TASKS['mono']
+    loss, vals, out = train_step(model, torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), tasks,
+                                 drop_mask=torch.from_numpy(masks).cuda() if p > 0 else None)
+    tsd = T.to_torch(sd, requires_grad=True)
+    ref_out = T.model_forward(tsd, torch.from_numpy(x), training=True, p_dropout=p,
+                              masks=[torch.from_numpy(m) for m in masks] if p > 0 else None)
+    ref_loss, ref_vals = T.multi_task_loss(ref_out, torch.from_numpy(y), tasks)
+    ref_loss.backward()
+    assert np.allclose(out.cpu().numpy(), ref_out.detach().numpy(), rtol=2e-5, atol=2e-5)
+    assert abs(float(loss) - float(ref_loss)) <= 5e-6 * abs(float(ref_loss))
+    for n, prm in model.named_parameters():
+        _cmp_grad(n, prm.grad.cpu().numpy(), tsd[n].grad.numpy())
+    for n, b in model.named_buffers():
+        if 'num_batches' not in n:
+            assert np.allclose(b.cpu().numpy(), tsd[n].detach().numpy(), rtol=2e-5, atol=2e-6), n
+
+
+def test_train_dropout_rng_consistency():
+    """In-kernel counter RNG: forward and backward regenerate the same masks (gradient of sum(out) wrt w_fin.bias is
+    exactly B), keep-rate ~ 1-p, and a fixed seed is reproducible."""
+    from monoloco_b200.train.fused import fused_train_forward
+    from monoloco_b200 import synthetic
+    model, _ = _model(34, 9, 256, 2, 8, p_dropout=0.3)
+    model.train()
+    x = torch.from_numpy(synthetic.make_inputs(500, 34, seed=1)).cuda()
+    a = fused_train_forward(model, x, seed=11)
+    b = fused_train_forward(model, x, seed=11)
+    c = fused_train_forward(model, x, seed=12)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a.sum().backward()
+    assert torch.allclose(model.w_fin.bias.grad, torch.full((8,), 500.0, device='cuda'))
+    assert float(model.w1.weight.grad.abs().sum()) > 0
+
+
+def test_optimizer_steps_reduce_loss():
+    """A few Adam steps through the drop-in path (trainer.py:153-161 incl. clip_grad_norm_) lower the loss and the eval
+    forward picks up the new weights."""
+    from monoloco_b200 import synthetic
+    from monoloco_b200.train import CompositeLoss, MultiTaskLoss
+    model, _ = _model(34, 9, 256, 2, 9, p_dropout=0.2)
+    tasks = TASKS['mono']
+    mt = MultiTaskLoss(*CompositeLoss(tasks)(), (1,) * len(tasks), tasks)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x = torch.from_numpy(synthetic.make_inputs(512, 34, seed=2)).cuda()
+    y = torch.from_numpy(synthetic.make_labels(512, seed=3)).cuda()
+    losses = []
+    for _ in range(12):
+        model.train()
+        opt.zero_grad()
+        loss, _ = mt(model(x), y, phase='train')
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 3)
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
+    model.eval()
+    with torch.no_grad():
+        e1 = model(x)
+        model.w_fin.bias.add_(0.5)
+        e2 = model(x)
+    assert torch.allclose(e2[:, :8], e1[:, :8] + 0.5, atol=1e-5)
