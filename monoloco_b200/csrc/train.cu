@@ -240,14 +240,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
     const int nwarps = L >> 7;  // active consumer warps (one per 128 columns)
     constexpr int ROWS = 2 * TM;
 
-    float* act = reinterpret_cast<float*>(smem_raw);      // [L][MP]; its head doubles as the dW A-stage buffer
-    float* outs = act + (size_t)L * MP;                    // [MP][OUT_LD]
+    float* act = reinterpret_cast<float*>(smem_raw);      // [L][MP]; its head doubles as the dW A-stage / PACK transpose buffer
+    const int act_floats = max(L * MP, 8 * 32 * 33);
+    float* outs = act + act_floats;                        // [MP][OUT_LD]
     float* ring = outs + MP * OUT_LD;                      // [NSTAGE][KC][L]
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTAGE * KC * L);
     uint64_t* empty = full + NSTAGE;
     volatile int* released = reinterpret_cast<volatile int*>(empty + NSTAGE);
 
-    for (int i = tid; i < L * MP + MP * OUT_LD; i += blockDim.x) act[i] = 0.f;
+    for (int i = tid; i < act_floats + MP * OUT_LD; i += blockDim.x) act[i] = 0.f;
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(&full[s], 1);
@@ -786,7 +787,8 @@ static int tfail(const std::string& m) {
 void mlb_count_launch();
 
 static size_t train_smem_bytes(int L) {
-    size_t fl = (size_t)L * MP + MP * OUT_LD + (size_t)NSTAGE * KC * L;
+    size_t actf = (size_t)L * MP > 8 * 32 * 33 ? (size_t)L * MP : 8 * 32 * 33;
+    size_t fl = actf + MP * OUT_LD + (size_t)NSTAGE * KC * L;
     return fl * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 16;
 }
 

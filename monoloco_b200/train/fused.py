@@ -10,6 +10,7 @@ Two ways in, both replacing trainer.py:153-161 (`outputs = model(inputs)`, `mt_l
 Optimizer / clip_grad_norm_ / scheduler stay PyTorch (trainer.py:159-161).
 """
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -87,6 +88,7 @@ def _fill(model, ws, x, out, grads=None, g_out=None, labels=None, tasks=None, sc
     a.n_rows, a.input_size, a.output_size = x.shape[0], model.stereo_size, model.output_size + 1
     a.linear_size, a.n_blocks, a.aux_block = model.linear_size, nb, nb - 2
     a.update_running_stats = int(update_running)
+    a.rows_per_group = int(os.environ.get('MLB_TRAIN_ROWS_PER_GROUP', '0'))  # 0 = auto; tests sweep 8..16
     a.p_dropout, a.bn_eps, a.bn_momentum = float(model.p_dropout), 1e-5, 0.1
     a.drop_seed = int(drop_seed)
     if drop_mask is not None:
