@@ -199,6 +199,9 @@ void mlb_train_destroy(mlb_train_handle h);
 int mlb_train_forward(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
 int mlb_train_backward(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
 int mlb_train_step(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream);
+/* profiling aid: wall time (ns) of every phase of the most recent launch (synchronises the device);
+ * returns the number of phases written. types: 0 PACK, 1 FWD, 2 FWD_FINAL, 3 BWD_INIT, 4 BWD_HEAD, 5 BWD, 6 DW. */
+int mlb_train_phase_times(mlb_train_handle h, int max_n, double* out_ns, int* types, int* blks);
 
 /* ---- NVLink peer buffers for the fused all-gather (cudaIpc*, one process per GPU) ---- */
 #define MLB_IPC_HANDLE_BYTES 64

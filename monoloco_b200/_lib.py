@@ -19,7 +19,7 @@ FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM = 1, 2, 4
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
-           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_probe_ffma',
+           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_probe_ffma',
            'mlb_launch_count']
 
 
@@ -102,6 +102,7 @@ def lib():
     l.mlb_train_destroy.restype = None
     for fn in (l.mlb_train_forward, l.mlb_train_backward, l.mlb_train_step):
         fn.argtypes = [C.c_void_p, C.POINTER(MlbTrainArgs), C.POINTER(MlbTrainBlock), C.c_void_p]
+    l.mlb_train_phase_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     l.mlb_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     l.mlb_launch_count.restype = C.c_uint64
     if l.mlb_abi_version() != MLB_ABI_VERSION:

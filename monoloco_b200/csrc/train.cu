@@ -71,6 +71,7 @@ struct TrainParams {
     float4* ptab;      // [grid][L][2]
     unsigned* bar_counter;
     int* err_flag;
+    unsigned long long* phase_ns;  // [MAX_PHASES + 1] globaltimer at kernel start and after every phase barrier (CTA 0)
 };
 
 __device__ __forceinline__ bool keep_elem(const TrainParams& p, int site, int grow, int col) {
@@ -103,14 +104,21 @@ __device__ void train_producer(const TrainParams& p, float* ring, float* astage,
                                volatile int* released) {
     RingState rs = {0u, 0u, 0u};
     const int L = p.L;
+    bool waited_pack = false;
     auto acquire_slot = [&]() {
         if (rs.q >= NSTAGE) mbar_wait_backoff(&empty[rs.stage], rs.parity ^ 1, p.err_flag);
     };
     for (int ph = 0; ph < p.n_phases; ++ph) {
         const int type = p.phase_type[ph], bi = p.phase_blk[ph];
         if (type != PH_FWD && type != PH_BWD && type != PH_DW) continue;
-        wait_released(released, ph);  // the grid barrier before this phase has been passed by this CTA
-        __threadfence();
+        // Wt is written by the PACK phase and the DW operands by the backward phases: wait for that phase's barrier.
+        // Native W (backward) and, after the first FWD phase, Wt are static -> the stream prefetches across barriers.
+        const bool depends = type == PH_DW || (type == PH_FWD && !waited_pack);
+        if (depends) {
+            wait_released(released, ph);
+            __threadfence();
+            if (type == PH_FWD) waited_pack = true;
+        }
         if (type == PH_FWD) {
             const TBlk& b = p.blk[bi];
             const uint32_t bytes = (uint32_t)(KC * L * sizeof(float));
@@ -276,6 +284,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
     const float invB = 1.0f / (float)p.n_rows;
     const int nfin = p.out_size - 1;
 
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        p.phase_ns[0] = t0;
+    }
     for (int ph = 0; ph < p.n_phases; ++ph) {
         const int type = p.phase_type[ph], bi = p.phase_blk[ph];
 
@@ -600,14 +613,24 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     for (int idx = tid; idx < (p.n_rows_pad - p.n_rows) * L; idx += NT) b.Gz[(size_t)p.n_rows * L + idx] = 0.f;
                 csync();
                 if (bi == 0) {
-                    // first layer: dW0[n][k] = sum_rows gz[row][n] * x[row][k]  (K = 34 | 68), no dX needed
-                    for (int n = tid; n < L; n += NT)
+                    // first layer: dW0[n][k] = sum_rows gz[row][n] * x[row][k]  (K = 34 | 68), no dX needed.
+                    // thread <-> feature n (coalesced re-read of the Gz rows just written), x tile broadcast from smem
+                    // (ring stage 0 is idle: the producer only restarts after this phase's barrier).
+                    float* xs = ring;
+                    for (int idx = tid; idx < rows_here * b.K; idx += NT)
+                        xs[idx] = __ldg(p.x + (size_t)row0 * p.in_size + idx);
+                    csync();
+                    for (int n = tid; n < L; n += NT) {
+                        float gzr[ROWS];
+#pragma unroll
+                        for (int rr = 0; rr < ROWS; ++rr) gzr[rr] = rr < rows_here ? b.Gz[(size_t)(row0 + rr) * L + n] : 0.f;
                         for (int k = 0; k < b.K; ++k) {
                             float a = 0.f;
-                            for (int rr = 0; rr < rows_here; ++rr)
-                                a = fmaf(act[n * MP + slot_of_row(rr, TM)], __ldg(p.x + (size_t)(row0 + rr) * p.in_size + k), a);
+#pragma unroll
+                            for (int rr = 0; rr < ROWS; ++rr) a = fmaf(gzr[rr], rr < rows_here ? xs[rr * b.K + k] : 0.f, a);
                             atomicAdd(b.dW + (size_t)n * b.K + k, a);
                         }
+                    }
                     csync();
                     continue;
                 }
@@ -752,6 +775,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
             }
         }
         grid_barrier(p, bar_target, released, tid);
+        if (blockIdx.x == 0 && tid == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            p.phase_ns[ph + 1] = t1;
+        }
     }
     // ---- finalise: per-task loss means (losses.py:139 torch.mean)
     if (blockIdx.x == 0 && p.labels != nullptr && tid < p.n_tasks) p.loss_vals[tid] = (float)(p.loss_acc[tid] / (double)p.n_rows);
@@ -771,6 +799,9 @@ struct mlb_train {
     float4* ptab;
     unsigned* bar;
     int* err;
+    unsigned long long* phase_ns;
+    int last_n_phases;
+    int last_phase_type[MAX_PHASES], last_phase_blk[MAX_PHASES];
 };
 
 extern thread_local std::string g_mlb_err;
@@ -827,6 +858,7 @@ extern "C" int mlb_train_create(int device, int max_rows, int input_size, int li
     TCU(cudaMalloc(&t->bar, sizeof(unsigned)));
     TCU(cudaMalloc(&t->err, sizeof(int)));
     TCU(cudaMemset(t->err, 0, sizeof(int)));
+    TCU(cudaMalloc(&t->phase_ns, (MAX_PHASES + 1) * sizeof(unsigned long long)));
     *out = t;
     return 0;
 }
@@ -837,7 +869,7 @@ extern "C" void mlb_train_destroy(mlb_train_handle t) {
     for (int i = 0; i < t->n_blocks; ++i) {
         cudaFree(t->Wt[i]), cudaFree(t->Z[i]), cudaFree(t->A[i]), cudaFree(t->G[i]), cudaFree(t->Gz[i]), cudaFree(t->stat[i]);
     }
-    cudaFree(t->g_out), cudaFree(t->loss_acc), cudaFree(t->ptab), cudaFree(t->bar), cudaFree(t->err);
+    cudaFree(t->g_out), cudaFree(t->loss_acc), cudaFree(t->ptab), cudaFree(t->bar), cudaFree(t->err), cudaFree(t->phase_ns);
     delete t;
 }
 
@@ -923,6 +955,7 @@ static int train_launch(mlb_train_handle t, const mlb_train_args* a, const mlb_t
         p.loss_vals = a->loss_vals;
     }
     p.loss_acc = t->loss_acc, p.ptab = t->ptab, p.bar_counter = t->bar, p.err_flag = t->err;
+    p.phase_ns = t->phase_ns;
 
     int np = 0;
     auto add = [&](int type, int blk) { p.phase_type[np] = type, p.phase_blk[np] = blk, np++; };
@@ -940,6 +973,9 @@ static int train_launch(mlb_train_handle t, const mlb_train_args* a, const mlb_t
     }
     p.n_phases = np;
     if (np > MAX_PHASES) return tfail("mlb_train: too many phases");
+    t->last_n_phases = np;
+    memcpy(t->last_phase_type, p.phase_type, sizeof(int) * np);
+    memcpy(t->last_phase_blk, p.phase_blk, sizeof(int) * np);
 
     TCU(cudaMemsetAsync(t->bar, 0, sizeof(unsigned), st));
     const size_t smem = train_smem_bytes(a->linear_size);
@@ -955,6 +991,22 @@ static int train_launch(mlb_train_handle t, const mlb_train_args* a, const mlb_t
     if (e != cudaSuccess) return tfail(std::string("loco_train_kernel launch: ") + cudaGetErrorString(e));
     mlb_count_launch();
     return 0;
+}
+
+// per-phase wall time (ns) of the most recent launch on this handle: out_ns[i] = duration of phase i, types/blks describe it
+extern "C" int mlb_train_phase_times(mlb_train_handle t, int max_n, double* out_ns, int* types, int* blks) {
+    if (!t || !out_ns) return tfail("mlb_train_phase_times: bad argument");
+    TCU(cudaSetDevice(t->device));
+    TCU(cudaDeviceSynchronize());
+    unsigned long long ts[MAX_PHASES + 1];
+    TCU(cudaMemcpy(ts, t->phase_ns, sizeof(ts), cudaMemcpyDeviceToHost));
+    int n = t->last_n_phases < max_n ? t->last_n_phases : max_n;
+    for (int i = 0; i < n; ++i) {
+        out_ns[i] = (double)(ts[i + 1] - ts[i]);
+        if (types) types[i] = t->last_phase_type[i];
+        if (blks) blks[i] = t->last_phase_blk[i];
+    }
+    return n;
 }
 
 extern "C" int mlb_train_forward(mlb_train_handle h, const mlb_train_args* a, const mlb_train_block* blocks, void* stream) {

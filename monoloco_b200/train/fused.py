@@ -199,3 +199,14 @@ def train_step(model, x, labels, tasks, lambdas=None, log_sigmas=None, drop_mask
         g = 1.0 - 2.0 * weighted
         log_sigmas.grad = g if (log_sigmas.grad is None or not accumulate) else log_sigmas.grad + g
     return loss, [weighted[i] for i in range(len(tasks))], out
+
+
+def phase_times(model):
+    """[(phase type name, block, ms)] of the most recent train launch of `model` (profiling aid)."""
+    ws = _WS.get(model)
+    names = ['PACK', 'FWD', 'FWD_FINAL', 'BWD_INIT', 'BWD_HEAD', 'BWD', 'DW']
+    ns = (C.c_double * 64)()
+    ty = (C.c_int * 64)()
+    bk = (C.c_int * 64)()
+    n = ws.lib.mlb_train_phase_times(ws.h, 64, ns, ty, bk)
+    return [(names[ty[i]], bk[i], ns[i] * 1e-6) for i in range(n)]

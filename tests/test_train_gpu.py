@@ -102,14 +102,16 @@ def _cmp_grad_statistical(name, got, ref):
     """Full-size rule.  A training step at B=4096, L=1024 takes 33 M ReLU / |.| sign decisions; O(10) borderline units
     (|y| ~ 1e-7) resolve differently between ANY two fp32 summation orders, and each flips one rank-one gradient term.
     The torch oracle itself moves by rel-L2 5e-4..1e-3 when the batch rows are merely reversed (measured in
-    DESIGN.md §5), so full-size gradients are held to rel-L2 <= 3e-3 and >= 90 % of elements inside the tight rule."""
+    DESIGN.md §5), so full-size gradients are held to rel-L2 <= 3e-3 and cosine >= 1 - 1e-5 (the tight rule is enforced at B <= 1000)."""
     got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     scale = max(float(np.abs(ref).max()), 1e-12)
-    tight = np.abs(got - ref) <= 1e-4 * np.abs(ref) + 2e-5 * scale + 2e-7
-    assert tight.mean() >= 0.90, (name, float(tight.mean()))
     nrm = float(np.linalg.norm(ref))
     if nrm > 1e-5 * np.sqrt(ref.size):
         assert float(np.linalg.norm(got - ref)) / nrm <= 3e-3, (name, float(np.linalg.norm(got - ref)) / nrm)
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * nrm))
+        assert cos >= 1.0 - 1e-5, (name, cos)
+    else:
+        assert np.abs(got - ref).max() <= 2e-5 * scale + 2e-7, name
 
 
 @pytest.mark.parametrize('tm', [10, 12, 14, 16])

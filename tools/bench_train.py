@@ -32,6 +32,8 @@ for B in [int(v) for v in (sys.argv[1:] or ['4096', '512'])]:
     y = torch.from_numpy(synthetic.make_labels(B, seed=4)).cuda()
     mt = MultiTaskLoss(*CompositeLoss(tasks)(), (1,) * len(tasks), tasks)
     t_fused = timeit(lambda: train_step(m, x, y, tasks))
+    from monoloco_b200.train.fused import phase_times
+    print('   phases (ms):', ' '.join('%s%d:%.3f' % (n, b, ms) for n, b, ms in phase_times(m)))
 
     def dropin():
         m.zero_grad(set_to_none=True)
