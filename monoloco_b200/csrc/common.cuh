@@ -133,18 +133,22 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
     return d;
 }
 
-// ---- counter-based RNG for the MC-dropout keep mask (net.py:135-161) ----
-__device__ __forceinline__ uint32_t mix32(uint64_t x) {
-    x ^= x >> 33;
-    x *= 0xff51afd7ed558ccdULL;
-    x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ULL;
-    x ^= x >> 33;
-    return (uint32_t)x;
+// ---- counter-based RNG for the dropout keep masks (net.py:135-161 MC dropout; nn.Dropout in training):
+// murmur3 fmix32 of (seed, site, row, col) -- regenerated identically wherever the mask is needed (forward, backward)
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {  // 64-bit counter -> 32 random bits (Laplace sampler)
+    return fmix32((uint32_t)x ^ fmix32((uint32_t)(x >> 32) + 0x9E3779B9u));
 }
 __device__ __forceinline__ bool keep_draw(uint64_t seed, uint32_t site, uint32_t row, uint32_t col, float p) {
-    uint64_t ctr = ((uint64_t)row << 32) | ((uint64_t)site << 24) | (uint64_t)col;
-    uint32_t r = mix32(ctr ^ (seed * 0x9E3779B97F4A7C15ULL));
+    const uint32_t s = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
+    const uint32_t r = fmix32(s ^ (row * 0x9E3779B1u) ^ fmix32(col * 0x85EBCA77u + site * 0xC2B2AE3Du + 0x27D4EB2Fu));
     return (float)(r >> 8) * (1.0f / 16777216.0f) >= p;
 }
 

@@ -142,15 +142,19 @@ __device__ void train_producer(const TrainParams& p, float* ring, float* astage,
                                      &full[rs.stage]);
                         ring_advance(rs);
                     }
-        } else {  // PH_DW
+        } else {  // PH_DW: stream-K split of the linearised (item, b-chunk) space -> every CTA gets the same number of chunks
             const int n_items = (p.n_blocks - 1) * (L / 32);
             const int nchunks = p.n_rows_pad / KC;
+            const long long total = (long long)n_items * nchunks;
+            const long long u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
             const uint32_t bytes = (uint32_t)(KC * L * sizeof(float) + KC * 32 * sizeof(float));
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (long long u = u0; u < u1;) {
+                const int item = (int)(u / nchunks), c0 = (int)(u % nchunks);
+                const int c1 = (int)min((long long)nchunks, c0 + (u1 - u));
                 const int b_i = 1 + item / (L / 32), n0 = (item % (L / 32)) * 32;
                 const TBlk& b = p.blk[b_i];
                 const float* ain = p.blk[b_i - 1].Aout;
-                for (int ch = 0; ch < nchunks; ++ch) {
+                for (int ch = c0; ch < c1; ++ch) {
                     acquire_slot();
                     mbar_expect_tx(&full[rs.stage], bytes);
                     tma_bulk_g2s(ring + (size_t)rs.stage * KC * L, ain + (size_t)ch * KC * L, KC * L * sizeof(float),
@@ -161,6 +165,7 @@ __device__ void train_producer(const TrainParams& p, float* ring, float* astage,
                                      32 * sizeof(float), &full[rs.stage]);
                     ring_advance(rs);
                 }
+                u += c1 - c0;
             }
         }
     }
@@ -321,6 +326,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 for (int f = blockIdx.x * NT + tid; f < L; f += gridDim.x * NT) b.db[f] = 0.f;
             }
             for (int f = blockIdx.x * NT + tid; f < L * p.blk[0].K; f += gridDim.x * NT) p.blk[0].dW[f] = 0.f;
+            for (int b_i = 1; b_i < p.n_blocks; ++b_i) {
+                float4* dw4 = reinterpret_cast<float4*>(p.blk[b_i].dW);
+                for (int f = blockIdx.x * NT + tid; f < L * L / 4; f += gridDim.x * NT) dw4[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             for (int f = blockIdx.x * NT + tid; f < L * nfin; f += gridDim.x * NT) p.dW_fin[f] = 0.f;
             for (int f = blockIdx.x * NT + tid; f < L; f += gridDim.x * NT) p.dW_aux[f] = 0.f;
             if (blockIdx.x == 0 && tid < nfin) p.db_fin[tid] = 0.f;
@@ -350,16 +359,22 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     }
                 } else {
                     const TBlk& pb = p.blk[prev];
+                    // __restrict__ views: lets the unrolled iterations issue all their L2 loads before the first store
+                    const float* __restrict__ Zp = pb.Z;
+                    float* __restrict__ Ap = pb.Aout;
+                    const float* __restrict__ Rp = pb.res_src >= 0 ? p.blk[pb.res_src].Aout : nullptr;
+                    const float4* __restrict__ pt = ptab;
+#pragma unroll 4
                     for (int k8 = warp; k8 < L / 8; k8 += 8) {
                         float h[8];
                         if (valid) {
                             if (pb.has_bn) {
-                                const float4 z0 = *reinterpret_cast<const float4*>(pb.Z + grow * L + k8 * 8);
-                                const float4 z1 = *reinterpret_cast<const float4*>(pb.Z + grow * L + k8 * 8 + 4);
+                                const float4 z0 = *reinterpret_cast<const float4*>(Zp + grow * L + k8 * 8);
+                                const float4 z1 = *reinterpret_cast<const float4*>(Zp + grow * L + k8 * 8 + 4);
                                 const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
                                 float res[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                                if (pb.res_src >= 0) {
-                                    const float* ra = p.blk[pb.res_src].Aout + grow * L + k8 * 8;
+                                if (Rp != nullptr) {
+                                    const float* ra = Rp + grow * L + k8 * 8;
                                     const float4 r0 = *reinterpret_cast<const float4*>(ra);
                                     const float4 r1 = *reinterpret_cast<const float4*>(ra + 4);
                                     res[0] = r0.x, res[1] = r0.y, res[2] = r0.z, res[3] = r0.w;
@@ -367,18 +382,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                                 }
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
-                                    const float4 t = ptab[2 * (k8 * 8 + e)];  // mean, invstd, gamma, beta
+                                    const float4 t = pt[2 * (k8 * 8 + e)];  // mean, invstd, gamma, beta
                                     const float zh = (z[e] - t.x) * t.y;
                                     float y = fmaxf(fmaf(zh, t.z, t.w), 0.f);
                                     y = keep_elem(p, pb.bn_index, (int)grow, k8 * 8 + e) ? y * inv_keep : 0.f;
                                     h[e] = y + res[e];
                                 }
-                                float* dst = pb.Aout + grow * L + k8 * 8;
+                                float* dst = Ap + grow * L + k8 * 8;
                                 *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
                                 *reinterpret_cast<float4*>(dst + 4) = make_float4(h[4], h[5], h[6], h[7]);
                             } else {
-                                const float4 a0 = *reinterpret_cast<const float4*>(pb.Aout + grow * L + k8 * 8);
-                                const float4 a1 = *reinterpret_cast<const float4*>(pb.Aout + grow * L + k8 * 8 + 4);
+                                const float4 a0 = *reinterpret_cast<const float4*>(Ap + grow * L + k8 * 8);
+                                const float4 a1 = *reinterpret_cast<const float4*>(Ap + grow * L + k8 * 8 + 4);
                                 h[0] = a0.x, h[1] = a0.y, h[2] = a0.z, h[3] = a0.w;
                                 h[4] = a1.x, h[5] = a1.y, h[6] = a1.z, h[7] = a1.w;
                             }
@@ -575,26 +590,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 const bool valid = slot_valid<TM>(lane, rows_here, r);
                 const size_t grow = (size_t)row0 + r;
                 // ---- prologue: gz = gamma*invstd*(gy - mean(gy) - zhat*mean(gy*zhat)) -> Gz (global) and act (k-major)
+                const float* __restrict__ Zp = b.Z;
+                const float* __restrict__ Gp = b.G;
+                float* __restrict__ Gzp = b.Gz;
+                const float4* __restrict__ pt = ptab;
+#pragma unroll 4
                 for (int k8 = warp; k8 < L / 8; k8 += 8) {
                     float gz[8];
                     if (valid) {
-                        const float4 z0 = *reinterpret_cast<const float4*>(b.Z + grow * L + k8 * 8);
-                        const float4 z1 = *reinterpret_cast<const float4*>(b.Z + grow * L + k8 * 8 + 4);
-                        const float4 g0 = *reinterpret_cast<const float4*>(b.G + grow * L + k8 * 8);
-                        const float4 g1 = *reinterpret_cast<const float4*>(b.G + grow * L + k8 * 8 + 4);
+                        const float4 z0 = *reinterpret_cast<const float4*>(Zp + grow * L + k8 * 8);
+                        const float4 z1 = *reinterpret_cast<const float4*>(Zp + grow * L + k8 * 8 + 4);
+                        const float4 g0 = *reinterpret_cast<const float4*>(Gp + grow * L + k8 * 8);
+                        const float4 g1 = *reinterpret_cast<const float4*>(Gp + grow * L + k8 * 8 + 4);
                         const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
                         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float4 t = ptab[2 * (k8 * 8 + e)];
-                            const float4 u = ptab[2 * (k8 * 8 + e) + 1];
+                            const float4 t = pt[2 * (k8 * 8 + e)];
+                            const float4 u = pt[2 * (k8 * 8 + e) + 1];
                             const float zh = (z[e] - t.x) * t.y;
                             const float y = fmaf(zh, t.z, t.w);
                             float gy = y > 0.f ? gg[e] : 0.f;
                             gy = keep_elem(p, b.bn_index, (int)grow, k8 * 8 + e) ? gy * inv_keep : 0.f;
                             gz[e] = t.z * t.y * (gy - u.x - zh * u.y);
                         }
-                        float* dst = b.Gz + grow * L + k8 * 8;
+                        float* dst = Gzp + grow * L + k8 * 8;
                         *reinterpret_cast<float4*>(dst) = make_float4(gz[0], gz[1], gz[2], gz[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(gz[4], gz[5], gz[6], gz[7]);
                     } else {
@@ -624,7 +644,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                         float gzr[ROWS];
 #pragma unroll
                         for (int rr = 0; rr < ROWS; ++rr) gzr[rr] = rr < rows_here ? b.Gz[(size_t)(row0 + rr) * L + n] : 0.f;
-                        for (int k = 0; k < b.K; ++k) {
+                        for (int kk = 0; kk < b.K; ++kk) {
+                            const int k = (kk + (int)blockIdx.x) % b.K;  // de-synchronise the CTAs' atomics on one address
                             float a = 0.f;
 #pragma unroll
                             for (int rr = 0; rr < ROWS; ++rr) a = fmaf(gzr[rr], rr < rows_here ? xs[rr * b.K + k] : 0.f, a);
@@ -753,25 +774,41 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
             // dW_i[n][k] = sum_b Gz_i[b][n] * A_{i-1}[b][k]: 32 n-rows x L columns per item, reduction streamed over b
             const int n_items = (p.n_blocks - 1) * (L / 32);
             const int nchunks = p.n_rows_pad / KC;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long long total = (long long)n_items * nchunks;
+            const long long u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+            for (long long u = u0; u < u1;) {
+                const int item = (int)(u / nchunks), c0 = (int)(u % nchunks);
+                const int c1 = (int)min((long long)nchunks, c0 + (u1 - u));
                 const int b_i = 1 + item / (L / 32), nb = (item % (L / 32)) * 32;
+                const bool whole = c0 == 0 && c1 == nchunks;  // this CTA owns the full reduction: plain stores
                 if (gemm_warp) {
                     unsigned long long acc2[8][8];
                     acc_zero<16>(acc2);
-                    tile_gemm<16>(acc2, nchunks, [&](int, unsigned stage) { return act + (size_t)stage * KC * 32; }, ring, full, empty,
-                                  rs, n0, g, lane, L, p.err_flag);
+                    tile_gemm<16>(acc2, c1 - c0, [&](int, unsigned stage) { return act + (size_t)stage * KC * 32; }, ring, full,
+                                  empty, rs, n0, g, lane, L, p.err_flag);
                     float* dst = p.blk[b_i].dW + (size_t)(nb + g * 16) * L + n0;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float lo[8], hi[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) unpack2(acc2[i][j], lo[j], hi[j]);
-                        *reinterpret_cast<float4*>(dst + (size_t)(2 * i) * L) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<float4*>(dst + (size_t)(2 * i) * L + 64) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                        *reinterpret_cast<float4*>(dst + (size_t)(2 * i + 1) * L) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<float4*>(dst + (size_t)(2 * i + 1) * L + 64) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                        float* d0 = dst + (size_t)(2 * i) * L;
+                        float* d1 = dst + (size_t)(2 * i + 1) * L;
+                        if (whole) {
+                            *reinterpret_cast<float4*>(d0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                            *reinterpret_cast<float4*>(d0 + 64) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                            *reinterpret_cast<float4*>(d1) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<float4*>(d1 + 64) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                atomicAdd(d0 + (j & 3) + (j >> 2) * 64, lo[j]);
+                                atomicAdd(d1 + (j & 3) + (j >> 2) * 64, hi[j]);
+                            }
+                        }
                     }
                 }
+                u += c1 - c0;
             }
         }
         grid_barrier(p, bar_target, released, tid);
