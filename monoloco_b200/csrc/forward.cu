@@ -30,62 +30,9 @@
 #include <mutex>
 #include <string>
 
-#include "common.cuh"
+#include "fwd_common.cuh"
 
 namespace mlb {
-
-struct FwdParams {
-    const float* blob;
-    mlb_op ops[MLB_MAX_OPS];
-    int n_ops, in_size, out_size, L, decode_kind;
-    int input_kind, flags, n_rows, n_right, n_tiles, kpad0;
-    float kinv[9];
-    float z_met;
-    const float* x;
-    const float* xr;
-    float* out_raw;
-    float* out_dec;
-    float* out_xyzc;
-    float* out_x;
-    const uint8_t* drop_mask;
-    unsigned long long drop_seed;
-    float p_drop;
-    float* res_scratch;
-    int* err_flag;
-    float* gather[MLB_MAX_PEERS];
-    int n_gather;
-    long long gather_row0;
-};
-
-// Laplace / spherical / orientation decode of one raw output row (process.py:231-278, 330-360; net.py:95-100).
-// Explicit __f*_rn intrinsics pin the reference's operation order (no FMA contraction).
-__device__ __forceinline__ void decode_row(int kind, int out_size, const float* o, float& x, float& y, float& z, float& d,
-                                           float& bi, float& yaw_p, float& yaw_o, float& aux) {
-    x = y = z = d = bi = yaw_p = yaw_o = aux = 0.f;
-    if (kind == MLB_DECODE_LOCO) {
-        const float th = o[0], ps = o[1];
-        d = o[2];
-        bi = __fmul_rn(expf(o[3]), d);                    // process.py:132
-        x = __fmul_rn(__fmul_rn(d, sinf(ps)), cosf(th));  // camera.py:232
-        y = __fmul_rn(d, cosf(ps));                       // camera.py:236
-        z = sqrtf(__fsub_rn(__fsub_rn(__fmul_rn(d, d), __fmul_rn(x, x)), __fmul_rn(y, y)));  // process.py:265
-        yaw_p = atan2f(o[7], o[8]);                       // process.py:272
-        if (out_size == 10) aux = 1.0f / (1.0f + expf(-o[9]));  // process.py:277
-    } else if (kind == MLB_DECODE_MONO) {
-        x = o[0], y = o[1], z = o[2];
-        d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));  // process.py:350
-        bi = __fmul_rn(expf(o[3]), o[2]);
-        yaw_p = atan2f(o[7], o[8]);
-    } else if (kind == MLB_DECODE_DB) {
-        d = o[0];
-        bi = __fmul_rn(expf(o[1]), o[0]);  // net.py:98
-    }
-    if (kind == MLB_DECODE_LOCO || kind == MLB_DECODE_MONO) {
-        yaw_o = __fadd_rn(yaw_p, atan2f(x, z));  // camera.py:203-204
-        if (yaw_o > 3.14159265358979323846f) yaw_o = __fsub_rn(yaw_o, 6.28318530717958647692f);
-        if (yaw_o < -3.14159265358979323846f) yaw_o = __fadd_rn(yaw_o, 6.28318530717958647692f);
-    }
-}
 
 // stand-alone decode of a raw [B, out] tensor (extract_outputs on outputs that did not come from the fused kernel)
 __global__ void decode_kernel(const float* __restrict__ raw, int n_rows, int out_size, int kind, float* __restrict__ dec) {
@@ -636,6 +583,11 @@ __global__ void __launch_bounds__(512) ffma2_probe_kernel(int iters, float* sink
 // ================================================================================================
 using namespace mlb;
 
+// forward_small.cu
+size_t mlb_small_smem_bytes(int L);
+cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, long long* slab_off, cudaStream_t st);
+cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st);
+
 struct mlb_model {
     mlb_model_desc desc;
     mlb_op ops[MLB_MAX_OPS];
@@ -643,6 +595,8 @@ struct mlb_model {
     int n_sms;
     float* blob_dev;
     size_t n_floats;
+    float* slab_dev;               // slab-major W^T copies for the small-batch cluster kernel (L == 1024 only)
+    long long slab_off[MLB_MAX_OPS];
     float* res_scratch;
     size_t res_floats;
     int* err_flag_dev;
@@ -722,6 +676,14 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     m->n_floats = n_floats;
     CU(cudaMalloc(&m->blob_dev, n_floats * sizeof(float)));
     CU(cudaMemcpy(m->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    if (L == 1024) {
+        size_t gemm_floats = 0;
+        for (int i = 0; i < desc->n_ops; ++i)
+            if (ops[i].type == MLB_OP_GEMM) gemm_floats += (size_t)ops[i].Kpad * L;
+        CU(cudaMalloc(&m->slab_dev, gemm_floats * sizeof(float)));
+        CU(mlb_small_pack(m->blob_dev, m->ops, desc->n_ops, L, m->slab_dev, m->slab_off, 0));
+        CU(cudaDeviceSynchronize());
+    }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
     CU(cudaMalloc(&m->err_flag_dev, sizeof(int)));
@@ -735,6 +697,8 @@ extern "C" int mlb_update_weights(mlb_handle h, const float* packed_host, size_t
     if (n_floats != h->n_floats) return fail("mlb_update_weights: blob size changed");
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (h->slab_dev)
+        CU(mlb_small_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->slab_dev, h->slab_off, (cudaStream_t)stream));
     return 0;
 }
 
@@ -742,6 +706,7 @@ extern "C" void mlb_destroy(mlb_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->blob_dev);
+    cudaFree(h->slab_dev);
     cudaFree(h->res_scratch);
     cudaFree(h->err_flag_dev);
     cudaFree(h->st_in);
@@ -824,6 +789,26 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     for (int i = 0; i < a->n_gather; ++i) {
         if (!a->gather[i]) return fail("mlb_forward: null gather pointer");
         p.gather[i] = a->gather[i];
+    }
+
+    // ---- small batches: 8-CTA cluster per 16 detections (forward_small.cu) when that finishes sooner than row tiles.
+    // Cost model (measured): cluster wave ~0.1 ms for up to 18 clusters; tile wave ~0.065 ms x rows-per-group.
+    if (h->slab_dev != nullptr && !(a->flags & MLB_FWD_FORCE_TILE) && !(a->flags & MLB_FWD_RES_TMEM)) {
+        const int n_clusters = (a->n_rows + 15) / 16;
+        const int conc = h->n_sms / 8;
+        const double t_small = 0.1 * ((n_clusters + conc - 1) / conc);
+        const int tm0 = pick_rows_per_group(a->n_rows, h->n_sms);
+        const long tiles0 = (a->n_rows + 2 * tm0 - 1) / (2 * tm0);
+        const double t_tile = 0.065 * tm0 * ((tiles0 + h->n_sms - 1) / h->n_sms) + 0.4;
+        if ((a->flags & MLB_FWD_FORCE_CLUSTER) || (a->rows_per_group == 0 && t_small < t_tile)) {
+            p.n_tiles = n_clusters;
+            cudaError_t es = mlb_small_launch(p, h->slab_dev, h->slab_off, n_clusters < conc ? n_clusters : conc, st);
+            if (es != cudaSuccess) return fail(std::string("loco_forward_cluster_kernel launch: ") + cudaGetErrorString(es));
+            g_launches++;
+            return 0;
+        }
+    } else if (a->flags & MLB_FWD_FORCE_CLUSTER) {
+        return fail("mlb_forward: the cluster kernel needs linear_size == 1024 and no MLB_FWD_RES_TMEM");
     }
 
     // consumer warpgroups (one active warp per 128 hidden columns) + one producer warpgroup (setmaxnreg split)

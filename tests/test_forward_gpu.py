@@ -218,3 +218,57 @@ def test_full_size_properties(mono1024):
     idx = np.random.RandomState(1).choice(4099, 512, replace=False)
     ok, worst = O.close(first.cpu().numpy()[idx], O.loco_model_forward(sd, base[idx]))
     assert ok, worst
+
+
+# ------------------------------------------------------------------------------------------------ small-batch kernel
+@pytest.mark.parametrize('B', [1, 5, 16, 17, 100, 256, 300, 1000])
+def test_cluster_kernel_batches_vs_oracle(mono1024, B):
+    """8-CTA-cluster kernel (forward_small.cu): column-split layers + DSMEM all-gather, forced on for every size
+    (B > 288 exercises the multi-tile loop of a cluster)."""
+    O, synthetic, engine, L_ = _mods()
+    sd, eng = mono1024
+    kps = synthetic.make_keypoints(B, seed=40 + B)
+    out = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_x=True, want_xyzc=True,
+                      kernel='cluster')
+    x = O.preprocess_monoloco(kps, synthetic.KITTI_K)
+    assert np.abs(out['x'].cpu().numpy() - x).max() < 6e-6
+    ref = O.loco_model_forward(sd, x)
+    ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+    assert ok, worst
+    _check_dec(O, out['dec'].cpu().numpy(), O.extract_outputs(ref), False)
+    tile = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_xyzc=True, kernel='tile')
+    assert torch.allclose(out['raw'], tile['raw'], rtol=2e-5, atol=2e-5) and torch.allclose(out['xyzc'], tile['xyzc'], rtol=1e-5, atol=1e-5)
+
+
+def test_cluster_kernel_stereo_dropout_and_legacy_models():
+    O, synthetic, engine, L_ = _mods()
+    f = np.load(os.path.join(GOLDEN, 'ref_loco_stereo.npz'))
+    sd = synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2)
+    eng = engine.LocoEngine(sd)
+    left, right = torch.from_numpy(f['left']).cuda(), torch.from_numpy(f['right']).cuda()
+    out = eng.forward(left, x_right=right, kk=f['K'], kind=L_.IN_KPS_STEREO, want_x=True, kernel='cluster')
+    assert np.abs(out['x'].cpu().numpy() - f['pairs_x']).max() < 6e-6
+    ok, worst = O.close(out['raw'].cpu().numpy(), f['pairs_raw'])
+    assert ok, worst
+    eng.close()
+    # MC-dropout masks and the in-kernel RNG are the same function of (seed, site, row, col) in both kernels
+    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+    eng = engine.LocoEngine(sd)
+    B = 77
+    masks = (np.random.RandomState(3).uniform(size=(2, B, 1024)) >= 0.2).astype(np.uint8)
+    x = synthetic.make_inputs(B, 34, seed=31)
+    ref = O.loco_model_forward(sd, x, drop_masks=(masks[0], masks[1]), p_dropout=0.2)
+    out = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_mask=torch.from_numpy(masks).cuda(), kernel='cluster')
+    ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+    assert ok, worst
+    a = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='cluster')['raw']
+    b = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='tile')['raw']
+    assert torch.allclose(a, b, rtol=2e-5, atol=2e-5)
+    eng.close()
+    # MonolocoModel (heads only at the end) through the cluster kernel
+    g = np.load(os.path.join(GOLDEN, 'ref_fwd_monoloco_l1024_o9.npz'))
+    eng = engine.LocoEngine(synthetic.make_state_dict('monoloco', 34, 9, 1024, 3, 3))
+    out = eng.forward(torch.from_numpy(g['x']).cuda(), kernel='cluster')
+    ok, worst = O.close(out['raw'].cpu().numpy(), g['out'])
+    assert ok, worst
+    eng.close()
