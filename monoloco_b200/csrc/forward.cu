@@ -587,6 +587,7 @@ using namespace mlb;
 size_t mlb_small_smem_bytes(int L);
 cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, long long* slab_off, cudaStream_t st);
 cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st);
+int mlb_small_max_clusters(int L);
 
 struct mlb_model {
     mlb_model_desc desc;
@@ -597,6 +598,7 @@ struct mlb_model {
     size_t n_floats;
     float* slab_dev;               // slab-major W^T copies for the small-batch cluster kernel (L == 1024 only)
     long long slab_off[MLB_MAX_OPS];
+    int small_conc;                // co-resident 8-CTA clusters (cudaOccupancyMaxActiveClusters)
     float* res_scratch;
     size_t res_floats;
     int* err_flag_dev;
@@ -683,6 +685,8 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
         CU(cudaMalloc(&m->slab_dev, gemm_floats * sizeof(float)));
         CU(mlb_small_pack(m->blob_dev, m->ops, desc->n_ops, L, m->slab_dev, m->slab_off, 0));
         CU(cudaDeviceSynchronize());
+        m->small_conc = mlb_small_max_clusters(L);
+        if (m->small_conc < 1) m->small_conc = 8;
     }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
@@ -792,14 +796,14 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     }
 
     // ---- small batches: 8-CTA cluster per 16 detections (forward_small.cu) when that finishes sooner than row tiles.
-    // Cost model (measured): cluster wave ~0.1 ms for up to 18 clusters; tile wave ~0.065 ms x rows-per-group.
+    // Cost model (measured): cluster wave 0.18 ms for `small_conc` clusters; tile wave 0.42 + 0.067 TM ms.
     if (h->slab_dev != nullptr && !(a->flags & MLB_FWD_FORCE_TILE) && !(a->flags & MLB_FWD_RES_TMEM)) {
         const int n_clusters = (a->n_rows + 15) / 16;
-        const int conc = h->n_sms / 8;
-        const double t_small = 0.1 * ((n_clusters + conc - 1) / conc);
+        const int conc = h->small_conc;
+        const double t_small = 0.185 * ((n_clusters + conc - 1) / conc);
         const int tm0 = pick_rows_per_group(a->n_rows, h->n_sms);
         const long tiles0 = (a->n_rows + 2 * tm0 - 1) / (2 * tm0);
-        const double t_tile = 0.065 * tm0 * ((tiles0 + h->n_sms - 1) / h->n_sms) + 0.4;
+        const double t_tile = (0.42 + 0.067 * tm0) * ((tiles0 + h->n_sms - 1) / h->n_sms);
         if ((a->flags & MLB_FWD_FORCE_CLUSTER) || (a->rows_per_group == 0 && t_small < t_tile)) {
             p.n_tiles = n_clusters;
             cudaError_t es = mlb_small_launch(p, h->slab_dev, h->slab_off, n_clusters < conc ? n_clusters : conc, st);

@@ -398,6 +398,28 @@ cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int 
     return cudaGetLastError();
 }
 
+// how many 8-CTA clusters of this kernel can be resident at once (GPC packing decides: measured 11-16 on a B200)
+int mlb_small_max_clusters(int L) {
+    const size_t smem = mlb_small_smem_bytes(L);
+    if (cudaFuncSetAttribute(loco_forward_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(CL * 64);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CL, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, loco_forward_cluster_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st) {
     SmallExtra ex;
     ex.slab = slab;
