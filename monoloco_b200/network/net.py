@@ -18,6 +18,7 @@ import torch
 from .. import _lib as L_
 from ..engine import dec_to_dict
 from ..utils import get_iou_matches, reorder_matches, get_keypoints, pixel_to_camera, xyz_from_distance
+from ..activity import social_interactions, is_raising_hand
 from .architectures import MonolocoModel, LocoModel
 
 
@@ -188,4 +189,21 @@ class Loco:
             dic_out['dds_real'].append(dd_real)
             dic_out['boxes_gt'].append(boxes_gt[idx_gt])
             dic_out['xyz_real'].append(xyz_real.squeeze().tolist())
+        return dic_out
+
+    @staticmethod
+    def social_distance(dic_out, args):
+        """net.py:250-265: flag every instance whose F-formation test fires."""
+        angles, dds, stds = dic_out['angles'], dic_out['dds_pred'], dic_out['stds_ale']
+        xz_centers = [[xx[0], xx[2]] for xx in dic_out['xyz_pred']]
+        dic_out['social_distance'] = [bool(social_interactions(idx, xz_centers, angles, dds, stds=stds,
+                                                               threshold_prob=args.threshold_prob,
+                                                               threshold_dist=args.threshold_dist, radii=args.radii))
+                                      for idx, _ in enumerate(dic_out['xyz_pred'])]
+        return dic_out
+
+    @staticmethod
+    def raising_hand(dic_out, keypoints):
+        """net.py:267-271."""
+        dic_out['raising_hand'] = [is_raising_hand(keypoint) for keypoint in keypoints]
         return dic_out

@@ -142,3 +142,15 @@ def test_product_never_imports_oracle():
             if fn.endswith('.py'):
                 src = open(os.path.join(dp, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), os.path.join(dp, fn)
+
+
+def test_activity_helpers(api):
+    """Loco.social_distance / raising_hand building blocks vs outputs of the reference's activity.py (fixture)."""
+    from monoloco_b200 import activity as M
+    with open(os.path.join(GOLDEN, 'ref_activity.json')) as f:
+        ref = json.load(f)
+    assert [M.is_raising_hand(k) for k in api['keypoints']] == ref['raising']
+    n = len(ref['centers'])
+    prob = [M.social_interactions(i, ref['centers'], ref['angles'], ref['dds'], stds=ref['stds']) for i in range(n)]
+    det = [M.social_interactions(i, ref['centers'], ref['angles'], ref['dds'], stds=ref['stds'], n_samples=1) for i in range(n)]
+    assert prob == ref['prob'] and det == ref['det']
