@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                         for (int j = 0; j < 8; ++j) acc2[i][j] = 0ull;
 
                     const float* a_ptr = in + g * 16;
+                    // two / four 8-k-step chunks per loop trip: halves the loop-carried register shuffling (measured:
+                    // 1.357 -> 1.264 -> 1.245 ms at B=4096; the 128-accumulator TM=16 tile spills beyond 2)
+#pragma unroll(TM <= 14 ? 4 : 2)
                     for (int ch = 0; ch < nchunks; ++ch, ++q) {
                         // invariant: chunk q has landed (waited for at the end of the previous iteration).
                         // Probe the NEXT stage now, non-blocking, so the mbarrier round trip hides under this chunk's FFMAs.
