@@ -100,12 +100,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def best_cpu_threads(fn, budget_s=6.0):
+    """The reference's CPU path is torch eager; on a many-core shared host `all threads` is often NOT its fastest
+    setting (128 threads on the GPU box: 2.4 s per 4096-batch vs 0.1-0.2 s at 16-32).  Give the baseline its best
+    thread count: try a few, keep the fastest, and report that count as `cores`."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], None
+    t_all = time.perf_counter()
+    for c in cands:
+        torch.set_num_threads(c)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if time.perf_counter() - t_all > budget_s:
+            break
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_rate(sd, x_np, budget_s=12.0, min_reps=3):
-    """detections/s of the reference's CPU path (torch eager, all host threads) on a bounded sample."""
+    """detections/s of the reference's CPU path (torch eager, best host thread count) on a bounded sample."""
     from oracle import torch_port as T  # the one place bench.py executes oracle/: the timed CPU baseline
     tsd = T.to_torch(sd)
     x = torch.from_numpy(x_np)
     with torch.no_grad():
+        best_cpu_threads(lambda: T.model_forward(tsd, x))
         for _ in range(2):
             T.model_forward(tsd, x)
         times = []
@@ -125,13 +148,14 @@ def run_reference(args, rank, world):
     from monoloco_b200 import synthetic
     from oracle import loco_oracle as O
     from oracle import torch_port as T
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
     B = args.batch
     kps = synthetic.make_keypoints(B, seed=0)
     tsd = T.to_torch(sd)
     times = []
     with torch.no_grad():
+        x0 = torch.from_numpy(O.preprocess_monoloco(kps, synthetic.KITTI_K))
+        best_cpu_threads(lambda: T.model_forward(tsd, x0))
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             x = O.preprocess_monoloco(kps, synthetic.KITTI_K)           # process.py:47-67
@@ -147,8 +171,9 @@ def run_reference(args, rank, world):
             "config": {"workload": "LocoModel mono 34->9 L=1024 x3 stages, pre-process + forward + decode, batch %d, CPU" % B,
                        "batch_per_step": B},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d steps x %d detections, torch-eager CPU restatement (oracle/torch_port.py)"
-                                       % (args.steps, B)},
+                             "host_cpus": os.cpu_count(),
+                             "sample": "%d steps x %d detections, torch-eager CPU restatement (oracle/torch_port.py), "
+                                       "best of several torch thread counts" % (args.steps, B)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -287,11 +312,11 @@ def main():
         }
         if not args.no_cpu_baseline:
             x = np.ascontiguousarray(synthetic.make_inputs(B, 34, seed=0))
-            torch.set_num_threads(os.cpu_count() or 1)
             rate, reps, med = cpu_reference_rate(sd, x)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "%d x batch-%d model forwards (oracle/torch_port.py), median %.1f ms"
-                                              % (reps, B, med * 1e3)}
+                                    "host_cpus": os.cpu_count(),
+                                    "sample": "%d x batch-%d model forwards (oracle/torch_port.py), median %.1f ms, best of "
+                                              "several torch thread counts" % (reps, B, med * 1e3)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
