@@ -141,6 +141,57 @@ def cpu_reference_rate(sd, x_np, budget_s=12.0, min_reps=3):
     return x_np.shape[0] / med, len(times), med
 
 
+def extras(eng, sd, dev):
+    """Side measurements outside the timed region (other BASELINE.json configs), device-timed, L2 warm:
+    small-batch latency (configs[0]/[1]: batch 1 / 256 -> cluster kernel), batch 65536, stereo 64x64 pairs + filter
+    (configs[2]), and the one-launch training step at batch 4096 (configs[3])."""
+    from monoloco_b200 import synthetic, _lib as L_
+    out = {}
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    try:
+        lat = {}
+        for b in (1, 16, 256, 65536):
+            x = torch.from_numpy(synthetic.make_keypoints(b, seed=2)).to(dev)
+            lat[str(b)] = timed(lambda: eng.forward(x, kk=synthetic.KITTI_K, kind=L_.IN_KPS), 20 if b <= 4096 else 3)
+        out["forward_ms_by_batch"] = lat
+        from monoloco_b200 import engine as E
+        seng = E.LocoEngine(synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2), device=dev)
+        le, ri = synthetic.make_keypoints(64, seed=3, right=True)
+        le, ri = torch.from_numpy(le).to(dev), torch.from_numpy(ri).to(dev)
+
+        def stereo():
+            o = seng.forward(le, x_right=ri, kk=synthetic.KITTI_K, kind=L_.IN_KPS_STEREO, want_xyzc=True)
+            seng.stereo_filter(o['raw'], o['dec'], 64, 64, xyzc=o['xyzc'])
+        out["stereo_64x64_pairs_plus_filter_ms"] = timed(stereo, 10)
+        seng.close()
+        from monoloco_b200.network.architectures import LocoModel
+        from monoloco_b200.train import train_step
+        m = LocoModel(34, 9, 1024, p_dropout=0.2, num_stage=3)
+        m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
+        m.to(dev).train()
+        xt = torch.from_numpy(synthetic.make_inputs(4096, 34, seed=3)).to(dev)
+        yt = torch.from_numpy(synthetic.make_labels(4096, seed=4)).to(dev)
+        tasks = ('d', 'x', 'y', 'h', 'w', 'l', 'ori')
+        ms = timed(lambda: train_step(m, xt, yt, tasks), 5)
+        out["train_step_b4096"] = {"ms": ms, "tflops": 3 * 16865280 * 4096 / ms / 1e9,
+                                   "what": "forward + MultiTaskLoss + backward + dW, one cooperative launch, fp32"}
+    except Exception as exc:  # side measurements must never break the contract line
+        out["error"] = repr(exc)
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path, timed on the host cores."""
     if rank != 0:
@@ -186,6 +237,7 @@ def main():
     ap.add_argument('--batch', type=int, default=4096, help='detections per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the small-batch latency / train-step side measurements')
     ap.add_argument('--rows-per-group', type=int, default=0)
     ap.add_argument('--gather', default='fused', choices=['fused', 'nccl'],
                     help='multi-GPU output all-gather: fused peer stores from the kernel epilogue, or NCCL')
@@ -310,6 +362,8 @@ def main():
                                   "peak_source": "measured in-run by mlb_probe_ffma (pure FFMA kernel)",
                                   "algorithmic_flops": flops}},
         }
+        if not args.no_extras:
+            line["extras"] = extras(eng, sd, dev)
         if not args.no_cpu_baseline:
             x = np.ascontiguousarray(synthetic.make_inputs(B, 34, seed=0))
             rate, reps, med = cpu_reference_rate(sd, x)

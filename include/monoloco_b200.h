@@ -85,9 +85,10 @@ enum { MLB_IN_X = 0,          /* pre-processed network input [B, input_size] (nn
 
 enum { MLB_FWD_ZERO_CENTER = 1, /* preprocess_monoloco(zero_center=True) (net.py:96, legacy)        */
        MLB_FWD_DROPOUT     = 2, /* MC-dropout pass: top-level dropout sites active (net.py:141)     */
-       MLB_FWD_RES_TMEM    = 4, /* stash the residual in Tensor Memory instead of the L2 scratch    */
+       MLB_FWD_RES_TMEM    = 4, /* stash the residual x of MyLinearSimple in Tensor Memory (default) */
        MLB_FWD_FORCE_TILE    = 8,  /* always use the throughput kernel (one CTA per row tile)        */
-       MLB_FWD_FORCE_CLUSTER = 16  /* always use the small-batch kernel (8-CTA cluster per 16 rows)  */ };
+       MLB_FWD_FORCE_CLUSTER = 16, /* always use the small-batch kernel (8-CTA cluster per 16 rows)  */
+       MLB_FWD_RES_SCRATCH   = 32  /* stash the residual in the L2-resident global scratch instead   */ };
 
 typedef struct mlb_forward_args {
     int32_t input_kind;     /* MLB_IN_*                                                             */

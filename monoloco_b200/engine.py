@@ -80,7 +80,7 @@ class LocoEngine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def forward(self, x, x_right=None, kk=None, kind=L_.IN_X, want_dec=True, want_xyzc=False, want_x=False,
-                zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=False,
+                zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=None,
                 gather_ptrs=None, gather_row0=0, kernel=None):
         """x: float32 CUDA tensor ([B,in] | [B,3,17] | left [L,3,17]).  Returns dict of CUDA tensors."""
         assert x.is_cuda and x.dtype == torch.float32
@@ -88,7 +88,7 @@ class LocoEngine:
         a = L_.MlbForwardArgs()
         a.input_kind = kind
         a.flags = (L_.FWD_ZERO_CENTER if zero_center else 0) | (L_.FWD_DROPOUT if dropout else 0) | \
-                  (L_.FWD_RES_TMEM if res_tmem else 0) | \
+                  (0 if res_tmem is None else (L_.FWD_RES_TMEM if res_tmem else L_.FWD_RES_SCRATCH)) | \
                   {None: 0, 'tile': L_.FWD_FORCE_TILE, 'cluster': L_.FWD_FORCE_CLUSTER}[kernel]
         if kind == L_.IN_KPS_STEREO:
             x_right = x_right.contiguous()

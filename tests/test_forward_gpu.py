@@ -93,8 +93,8 @@ def test_forward_residual_in_tensor_memory(mono1024):
     O, synthetic, engine, L_ = _mods()
     sd, eng = mono1024
     x = torch.from_numpy(synthetic.make_inputs(900, 34, seed=9)).cuda()
-    a = eng.forward(x, kernel='tile')['raw']
-    b = eng.forward(x, res_tmem=True, kernel='tile')['raw']
+    a = eng.forward(x, res_tmem=False, kernel='tile')['raw']  # L2-resident global scratch
+    b = eng.forward(x, res_tmem=True, kernel='tile')['raw']   # Tensor Memory (the default)
     assert torch.equal(a, b)  # same kernel, same summation order: the stash location must not change a bit
 
 
