@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -54,7 +53,8 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md): one persistent
+    `nvidia-smi -lms 20` process, started before and killed after the region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -63,26 +63,29 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(',')])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        self.proc = None
 
     def __enter__(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)  # first sample lands before the timed region starts
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        self.rows = [[c.strip() for c in ln.split(',')] for ln in out.strip().splitlines() if ln.strip()]
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
