@@ -186,14 +186,14 @@ class LocoEngine:
 
     def epistemic_std(self, x, n_dropout, n_samples=100, seed=1, kind=L_.IN_X, kk=None):
         """net.py:135-161: n_dropout stochastic forwards (top-level dropout on) -> (d, bi) -> Laplace sampling -> std.
-        Returns a CUDA tensor [B]."""
+        The passes are independent rows to the kernel: the inputs are replicated n_dropout times and run as ONE
+        launch (the dropout mask is a function of (seed, site, row, column), so every replica draws its own mask and
+        the weights are streamed once for all passes instead of once per pass).  Returns a CUDA tensor [B]."""
         B = x.shape[0]
-        d_bi = torch.empty((n_dropout, B, 2), dtype=torch.float32, device=self.device)
+        reps = x.repeat((n_dropout,) + (1,) * (x.dim() - 1))
+        out = self.forward(reps, kk=kk, kind=kind, dropout=True, drop_seed=seed)
         c0 = 0 if self.output_size == 2 else 2  # net.py:146-149: db = outputs[:, 0:2] (monoloco) | outputs[:, 2:4]
-        for n in range(n_dropout):
-            out = self.forward(x, kk=kk, kind=kind, dropout=True, drop_seed=seed * 1000003 + n)
-            d_bi[n, :, 0] = out['raw'][:, c0]
-            d_bi[n, :, 1] = out['dec'][:, 4]  # bi = exp(s) * d, decoded in-kernel (process.py:132)
+        d_bi = torch.stack((out['raw'][:, c0], out['dec'][:, 4]), dim=1).contiguous()  # [n_dropout * B, 2] = [N, B, 2]
         std = torch.empty((B,), dtype=torch.float32, device=self.device)
         if B:
             L_.check(self._lib.mlb_laplace_std(d_bi.data_ptr(), n_dropout, B, n_samples, int(seed), std.data_ptr(),
