@@ -14,10 +14,19 @@ from .packing import pack_state_dict
 DEC_COLS = ('x', 'y', 'z', 'd', 'bi', 'yaw_pred', 'yaw_orig', 'aux')
 
 
+_KINV_CACHE = {}
+
+
 def kinv_from_kk(kk):
-    """K^-1 (utils/camera.py:25) computed once on the host in float64, rounded to fp32."""
+    """K^-1 (utils/camera.py:25) computed once on the host in float64, rounded to fp32 (cached per K)."""
     k = np.asarray(kk.detach().cpu().numpy() if hasattr(kk, 'detach') else kk, dtype=np.float64).reshape(3, 3)
-    return np.linalg.inv(k).astype(np.float32).reshape(9)
+    key = k.tobytes()
+    v = _KINV_CACHE.get(key)
+    if v is None:
+        if len(_KINV_CACHE) > 64:
+            _KINV_CACHE.clear()
+        v = _KINV_CACHE[key] = np.linalg.inv(k).astype(np.float32).reshape(9)
+    return v
 
 
 class LocoEngine:

@@ -77,8 +77,8 @@ class Loco:
             return None
         eng = self.model.engine()
         with torch.no_grad():
-            kps = torch.tensor(keypoints, dtype=torch.float32).to(self.device)
             if self.net == 'monstereo':
+                kps = torch.tensor(keypoints, dtype=torch.float32).to(self.device)
                 if keypoints_r:
                     kps_r = torch.tensor(keypoints_r, dtype=torch.float32).to(self.device)
                 else:
@@ -90,7 +90,22 @@ class Loco:
                 dic_out['xyz_c'] = xyzc[:, 0:3].cpu()
                 n_out = kps.shape[0]  # net.py:130: outputs is the clustered 3-D tensor -> number of left poses
                 inputs = None
+            elif not self.epistemic and self.net != 'monoloco':
+                # per-image fast path: one C call does H2D (pinned staging), the fused kernel, D2H and the sync
+                out = self._forward_host_mono(eng, keypoints, kk)
+                raw, dec = out['raw'], out['dec']
+                if self.net == 'monoloco_p':
+                    r, d = raw, dec
+                    dic_out = {'xyz': r[:, 0:3], 'zb': r[:, 2:4], 'h': r[:, 4:5], 'w': r[:, 5:6], 'l': r[:, 6:7],
+                               'ori': r[:, 7:9], 'xyzd': d[:, 0:4], 'd': d[:, 3:4], 'bi': d[:, 4:5],
+                               'yaw': (d[:, 5:6], d[:, 6:7])}
+                else:
+                    dic_out = dec_to_dict(raw, dec, stereo=False)
+                dic_out['xyz_c'] = out['xyzc'][:, 0:3]
+                dic_out['epi'] = [0.] * raw.shape[0]
+                return dic_out
             else:
+                kps = torch.tensor(keypoints, dtype=torch.float32).to(self.device)
                 zero_center = self.net == 'monoloco'
                 out = eng.forward(kps, kk=kk, kind=L_.IN_KPS, want_xyzc=True, want_x=self.epistemic,
                                   zero_center=zero_center)
@@ -112,6 +127,23 @@ class Loco:
             else:
                 dic_out['epi'] = [0.] * n_out
         return dic_out
+
+    def _forward_host_mono(self, eng, keypoints, kk):
+        """Python lists -> pinned staging -> mlb_forward_host -> fresh CPU tensors (caller owns them, net.py contract)."""
+        import numpy as np
+        m = len(keypoints)
+        st = getattr(self, '_stage', None)
+        if st is None or st['cap'] < m:
+            cap = max(64, 1 << (m - 1).bit_length())
+            st = {'cap': cap, 'kps': torch.empty((cap, 3, 17), dtype=torch.float32).pin_memory(),
+                  'raw': torch.empty((cap, eng.output_size), dtype=torch.float32).pin_memory(),
+                  'dec': torch.empty((cap, 8), dtype=torch.float32).pin_memory(),
+                  'xyzc': torch.empty((cap, 4), dtype=torch.float32).pin_memory()}
+            self._stage = st
+        st['kps'][:m] = torch.from_numpy(np.asarray(keypoints, dtype=np.float32))
+        out = {'raw': st['raw'][:m], 'dec': st['dec'][:m], 'xyzc': st['xyzc'][:m]}
+        eng.forward_host(st['kps'][:m], kk=kk, kind=L_.IN_KPS, out=out)
+        return {k: v.clone() for k, v in out.items()}
 
     def epistemic_uncertainty(self, inputs):
         """net.py:135-161: n_dropout stochastic passes (top-level dropout on) + Laplace sampling -> std per instance."""
