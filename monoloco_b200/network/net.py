@@ -154,74 +154,59 @@ class Loco:
     # ------------------------------------------------------------------------------------------- post-process
     @staticmethod
     def post_process(dic_in, boxes, keypoints, kk, dic_gt=None, iou_min=0.3, reorder=True, verbose=False):
-        """net.py:163-248: final per-instance dictionary for visualisation / KITTI txt (host-side list logic)."""
-        dic_out = defaultdict(list)
+        """Final per-instance dictionary for visualisation / KITTI txt (same keys, order and values as net.py:163-248),
+        computed column-wise: instances matched to ground truth come first (left to right), then the rest."""
+        import numpy as np
+        res = defaultdict(list)
         if dic_in is None:
-            return dic_out
-        if dic_gt:
-            boxes_gt = dic_gt['boxes']
-            dds_gt = [el[3] for el in dic_gt['ys']]
-            matches = get_iou_matches(boxes, boxes_gt, iou_min=iou_min)
-            dic_out['gt'] = [True]
-            if verbose:
-                print("found {} matches with ground-truth".format(len(matches)))
-            idxs_matches = [el[0] for el in matches]
-            not_matches = [idx for idx, _ in enumerate(boxes) if idx not in idxs_matches]
-        else:
-            matches = []
-            not_matches = list(range(len(boxes)))
-            if verbose:
-                print("NO ground-truth associated")
+            return res
+        n = len(boxes)
+        matches = get_iou_matches(boxes, dic_gt['boxes'], iou_min=iou_min) if dic_gt else []
+        if verbose:
+            print("found {} matches with ground-truth".format(len(matches)) if dic_gt else "NO ground-truth associated")
+        taken = {i for i, _ in matches}
         if reorder and matches:
             matches = reorder_matches(matches, boxes, mode='left_right')
-        all_idxs = [idx for idx, _ in matches] + not_matches
-        dic_out['gt'] = [True] * len(matches) + [False] * len(not_matches)
+        order = [i for i, _ in matches] + [i for i in range(n) if i not in taken]
+        res['gt'] = [True] * len(matches) + [False] * (n - len(matches))
 
-        uv_shoulders = get_keypoints(keypoints, mode='shoulder').tolist()
-        uv_heads = get_keypoints(keypoints, mode='head').tolist()
-        uv_centers_t = get_keypoints(keypoints, mode='center')
-        uv_centers = uv_centers_t.tolist()
-        xy_centers = pixel_to_camera(uv_centers_t, kk, 1)
-        xyz_c = dic_in.get('xyz_c') if isinstance(dic_in, dict) else None  # computed by the fused kernel
-
-        for idx in all_idxs:
-            box = boxes[idx]
-            dd_pred = float(dic_in['d'][idx])
-            bi = float(dic_in['bi'][idx])
-            var_y = float(dic_in['epi'][idx])
-            if xyz_c is not None and len(xyz_c) == len(boxes):
-                xyz_pred = xyz_c[idx]
-            else:
-                xyz_pred = xyz_from_distance(dd_pred, xy_centers[idx])[0]
-            distance = math.sqrt(float(xyz_pred[0]) ** 2 + float(xyz_pred[1]) ** 2 + float(xyz_pred[2]) ** 2)
-            conf = 0.035 * (box[-1]) / (bi / distance)
-            dic_out['boxes'].append(box)
-            dic_out['confs'].append(conf)
-            dic_out['dds_pred'].append(dd_pred)
-            dic_out['stds_ale'].append(bi)
-            dic_out['stds_epi'].append(var_y)
-            dic_out['xyz_pred'].append(xyz_pred.squeeze().tolist())
-            dic_out['uv_kps'].append(keypoints[idx])
-            dic_out['uv_centers'].append([round(uv_centers[idx][0]), round(uv_centers[idx][1])])
-            dic_out['uv_shoulders'].append([round(uv_shoulders[idx][0]), round(uv_shoulders[idx][1])])
-            dic_out['uv_heads'].append([round(uv_heads[idx][0]), round(uv_heads[idx][1])])
-            try:
-                dic_out['angles'].append(float(dic_in['yaw'][0][idx]))
-                dic_out['angles_egocentric'].append(float(dic_in['yaw'][1][idx]))
-            except KeyError:
+        col = lambda key: np.asarray(dic_in[key], dtype=np.float64).reshape(-1)  # noqa: E731
+        dd, bi, epi = col('d'), col('bi'), np.asarray(dic_in['epi'], dtype=np.float64).reshape(-1)
+        centres = get_keypoints(keypoints, mode='center')
+        rays = pixel_to_camera(centres, kk, 1)  # bbox-centre rays at z = 1 (net.py:195)
+        if isinstance(dic_in, dict) and dic_in.get('xyz_c') is not None and len(dic_in['xyz_c']) == n:
+            xyz = dic_in['xyz_c']  # xyz_from_distance already evaluated by the fused kernel's epilogue
+        else:
+            xyz = xyz_from_distance(torch.as_tensor(dd, dtype=torch.float32), rays)
+        xyz64 = np.asarray(xyz, dtype=np.float64)
+        conf = 0.035 * np.asarray([b[-1] for b in boxes], dtype=np.float64) / (bi / np.sqrt((xyz64 ** 2).sum(1)))
+        pix = {name: np.asarray(get_keypoints(keypoints, mode=mode)).tolist()
+               for name, mode in (('uv_centers', 'center'), ('uv_shoulders', 'shoulder'), ('uv_heads', 'head'))}
+        has_yaw, has_aux = 'yaw' in dic_in, 'aux' in dic_in
+        for i in order:
+            res['boxes'].append(boxes[i])
+            res['confs'].append(float(conf[i]))
+            res['dds_pred'].append(float(dd[i]))
+            res['stds_ale'].append(float(bi[i]))
+            res['stds_epi'].append(float(epi[i]))
+            res['xyz_pred'].append(np.asarray(xyz[i]).reshape(-1).tolist())
+            res['uv_kps'].append(keypoints[i])
+            for name, pts in pix.items():
+                res[name].append([round(pts[i][0]), round(pts[i][1])])
+            res['angles']  # the reference's defaultdict access creates these keys even when the value is missing
+            if not has_yaw:
                 continue
-            try:
-                dic_out['aux'].append(float(dic_in['aux'][idx]))
-            except KeyError:
-                continue
-
-        for idx, idx_gt in matches:
-            dd_real = dds_gt[idx_gt]
-            xyz_real = xyz_from_distance(dd_real, xy_centers[idx])
-            dic_out['dds_real'].append(dd_real)
-            dic_out['boxes_gt'].append(boxes_gt[idx_gt])
-            dic_out['xyz_real'].append(xyz_real.squeeze().tolist())
-        return dic_out
+            res['angles'].append(float(dic_in['yaw'][0][i]))
+            res['angles_egocentric'].append(float(dic_in['yaw'][1][i]))
+            res['aux']
+            if has_aux:
+                res['aux'].append(float(dic_in['aux'][i]))
+        for i, j in matches:
+            d_real = dic_gt['ys'][j][3]
+            res['dds_real'].append(d_real)
+            res['boxes_gt'].append(dic_gt['boxes'][j])
+            res['xyz_real'].append(xyz_from_distance(d_real, rays[i]).squeeze().tolist())
+        return res
 
     @staticmethod
     def social_distance(dic_out, args):
