@@ -27,6 +27,8 @@ __device__ __forceinline__ void tile_gemm(unsigned long long (&acc2)[TM / 2][8],
                                           const float* ring, uint64_t* full, uint64_t* empty, RingState& rs, int n0, int g,
                                           int lane, int L, int* err_flag) {
     if (nchunks > 0 && !mbar_test_wait(&full[rs.stage], rs.parity)) mbar_wait(&full[rs.stage], rs.parity, err_flag);
+    // several chunks per loop trip: less loop-carried register shuffling (forward.cu measured 1.357 -> 1.245 ms with it)
+#pragma unroll(TM <= 14 ? 4 : 2)
     for (int ch = 0; ch < nchunks; ++ch) {
         unsigned nstage = rs.stage + 1, nparity = rs.parity;
         if (nstage == NSTAGE) nstage = 0, nparity ^= 1;

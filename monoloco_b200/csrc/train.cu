@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 csync();
                 if (tid < p.out_size)
                     for (int rr = 0; rr < rows_here; ++rr) dbacc += outs[rr * OUT_LD + tid];
-                for (int k = tid; k < L; k += NT) {
+                for (int kk = tid; kk < L; kk += NT) {
+                    const int k = (kk + (int)blockIdx.x * 64) % L;  // every CTA starts elsewhere: no 147-way atomic pile-up per address
                     float wf[OUT_LD];
                     for (int o = 0; o < nfin; ++o) wf[o] = __ldg(p.W_fin + (size_t)o * L + k);
                     const float4 t = ptab[2 * k];
