@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     float accf[OUT_LD];
                     for (int o = 0; o < nfin; ++o) accf[o] = 0.f;
                     float acca = 0.f, s3 = 0.f, s4 = 0.f;
+#pragma unroll 4
                     for (int rr = 0; rr < rows_here; ++rr) {
                         const size_t gr = (size_t)row0 + rr;
                         const float* go = outs + rr * OUT_LD;
@@ -623,12 +624,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                         for (int e = 0; e < 8; ++e) gz[e] = 0.f;
                     }
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        act[(k8 * 8 + e) * MP + lane] = gz[e];
-                        float sdb = gz[e];  // db = column sum of gz (nn.Linear.bias gradient)
-                        for (int sft = 16; sft > 0; sft >>= 1) sdb += __shfl_xor_sync(0xffffffffu, sdb, sft);
-                        if (lane == 0) atomicAdd(b.db + k8 * 8 + e, sdb);
-                    }
+                    for (int e = 0; e < 8; ++e) act[(k8 * 8 + e) * MP + lane] = gz[e];
+                    // nn.Linear.bias in front of a BatchNorm: db = sum_b gz = gamma*invstd*(S3 - B*c1 - c2*sum(zhat)) == 0
+                    // identically (the reference's autograd returns ~1e-9 rounding noise); db stays at the zero BWD_INIT wrote.
                 }
                 if (tile == p.n_tiles - 1)
                     for (int idx = tid; idx < (p.n_rows_pad - p.n_rows) * L; idx += NT) b.Gz[(size_t)p.n_rows * L + idx] = 0.f;
