@@ -541,37 +541,61 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 csync();
                 if (tid < p.out_size)
                     for (int rr = 0; rr < rows_here; ++rr) dbacc += outs[rr * OUT_LD + tid];
-                for (int kk = tid; kk < L; kk += NT) {
-                    const int k = (kk + (int)blockIdx.x * 64) % L;  // every CTA starts elsewhere: no 147-way atomic pile-up per address
-                    float wf[OUT_LD];
-                    for (int o = 0; o < nfin; ++o) wf[o] = __ldg(p.W_fin + (size_t)o * L + k);
-                    const float4 t = ptab[2 * k];
-                    float accf[OUT_LD];
-                    for (int o = 0; o < nfin; ++o) accf[o] = 0.f;
-                    float acca = 0.f, s3 = 0.f, s4 = 0.f;
-#pragma unroll 4
-                    for (int rr = 0; rr < rows_here; ++rr) {
-                        const size_t gr = (size_t)row0 + rr;
-                        const float* go = outs + rr * OUT_LD;
-                        const float a9 = lb.Aout[gr * L + k], a8 = ab.Aout[gr * L + k];
-                        float G = 0.f;
-                        for (int o = 0; o < nfin; ++o) {
-                            G = fmaf(go[o], wf[o], G);
-                            accf[o] = fmaf(go[o], a9, accf[o]);
-                        }
-                        acca = fmaf(go[nfin], a8, acca);
-                        lb.G[gr * L + k] = G;
-                        const float zh = (lb.Z[gr * L + k] - t.x) * t.y;
-                        const float y = fmaf(zh, t.z, t.w);
-                        float gy = y > 0.f ? G : 0.f;
-                        gy = keep_elem(p, lb.bn_index, (int)gr, k) ? gy * inv_keep : 0.f;
-                        s3 += gy;
-                        s4 = fmaf(gy, zh, s4);
+                // thread <-> up to 4 features k (coalesced rows); rows outer / features inner so that 12 independent
+                // L2 loads are in flight per iteration instead of 3
+                constexpr int KQ = 4;
+                int kq[KQ];
+                float wf[KQ][OUT_LD], accf[KQ][OUT_LD], acca[KQ], s3[KQ], s4[KQ];
+                float4 tq[KQ];
+#pragma unroll
+                for (int q = 0; q < KQ; ++q) {
+                    const int kk = tid + q * NT;
+                    kq[q] = kk < L ? (kk + (int)blockIdx.x * 64) % L : -1;  // every CTA starts elsewhere (atomics spread)
+                    acca[q] = s3[q] = s4[q] = 0.f;
+                    tq[q] = kq[q] >= 0 ? ptab[2 * kq[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int o = 0; o < OUT_LD; ++o) {
+                        accf[q][o] = 0.f;
+                        wf[q][o] = (kq[q] >= 0 && o < nfin) ? __ldg(p.W_fin + (size_t)o * L + kq[q]) : 0.f;
                     }
-                    for (int o = 0; o < nfin; ++o) atomicAdd(p.dW_fin + (size_t)o * L + k, accf[o]);
-                    atomicAdd(p.dW_aux + k, acca);
-                    atomicAdd(&lb.stat[2 * L + k], (double)s3);
-                    atomicAdd(&lb.stat[3 * L + k], (double)s4);
+                }
+                for (int rr = 0; rr < rows_here; ++rr) {
+                    const size_t gr = (size_t)row0 + rr;
+                    const float* go = outs + rr * OUT_LD;
+                    float a9[KQ], a8[KQ], zz[KQ];
+#pragma unroll
+                    for (int q = 0; q < KQ; ++q) {
+                        const size_t off = gr * L + (kq[q] >= 0 ? kq[q] : 0);
+                        a9[q] = lb.Aout[off], a8[q] = ab.Aout[off], zz[q] = lb.Z[off];
+                    }
+#pragma unroll
+                    for (int q = 0; q < KQ; ++q) {
+                        if (kq[q] < 0) continue;
+                        float G = 0.f;
+#pragma unroll
+                        for (int o = 0; o < OUT_LD; ++o) {
+                            if (o < nfin) {
+                                G = fmaf(go[o], wf[q][o], G);
+                                accf[q][o] = fmaf(go[o], a9[q], accf[q][o]);
+                            }
+                        }
+                        acca[q] = fmaf(go[nfin], a8[q], acca[q]);
+                        lb.G[gr * L + kq[q]] = G;
+                        const float zh = (zz[q] - tq[q].x) * tq[q].y;
+                        const float y = fmaf(zh, tq[q].z, tq[q].w);
+                        float gy = y > 0.f ? G : 0.f;
+                        gy = keep_elem(p, lb.bn_index, (int)gr, kq[q]) ? gy * inv_keep : 0.f;
+                        s3[q] += gy;
+                        s4[q] = fmaf(gy, zh, s4[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < KQ; ++q) {
+                    if (kq[q] < 0) continue;
+                    for (int o = 0; o < nfin; ++o) atomicAdd(p.dW_fin + (size_t)o * L + kq[q], accf[q][o]);
+                    atomicAdd(p.dW_aux + kq[q], acca[q]);
+                    atomicAdd(&lb.stat[2 * L + kq[q]], (double)s3[q]);
+                    atomicAdd(&lb.stat[3 * L + kq[q]], (double)s4[q]);
                 }
                 csync();
             }
