@@ -206,6 +206,16 @@ int mlb_train_step(mlb_train_handle h, const mlb_train_args* a, const mlb_train_
  * returns the number of phases written. types: 0 PACK, 1 FWD, 2 FWD_FINAL, 3 BWD_INIT, 4 BWD_HEAD, 5 BWD, 6 DW. */
 int mlb_train_phase_times(mlb_train_handle h, int max_n, double* out_ns, int* types, int* blks);
 
+/* ---- optimizer side of the train step (trainer.py:159-160): clip_grad_norm_(params, max_norm) + Adam.step() over a
+ * list of fp32 tensors (device pointers, host arrays of pointers / sizes), two multi-tensor launches, no host sync.
+ * clip_mask[i] != 0: tensor i takes part in the gradient norm and is scaled by the clip coefficient (the reference clips
+ * model.parameters() only; AutoTune's log_sigmas are optimised but not clipped).  max_norm <= 0 disables clipping.
+ * `step` is Adam's 1-based step count; sqnorm_scratch_dev is one device double. */
+int mlb_adam_clip_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* sizes, const int32_t* clip_mask, float max_norm, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int64_t step, double* sqnorm_scratch_dev,
+                       void* stream);
+
 /* ---- NVLink peer buffers for the fused all-gather (cudaIpc*, one process per GPU) ---- */
 #define MLB_IPC_HANDLE_BYTES 64
 /* cudaMalloc `bytes` on `device` (zero-filled) and export an IPC handle for the other ranks. */

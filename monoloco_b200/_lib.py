@@ -19,7 +19,8 @@ FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, F
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
-           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_probe_ffma',
+           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_adam_clip_step',
+           'mlb_probe_ffma',
            'mlb_launch_count']
 
 
@@ -103,6 +104,9 @@ def lib():
     for fn in (l.mlb_train_forward, l.mlb_train_backward, l.mlb_train_step):
         fn.argtypes = [C.c_void_p, C.POINTER(MlbTrainArgs), C.POINTER(MlbTrainBlock), C.c_void_p]
     l.mlb_train_phase_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.mlb_adam_clip_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                     C.c_void_p, C.c_void_p]
     l.mlb_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]
     l.mlb_launch_count.restype = C.c_uint64
     if l.mlb_abi_version() != MLB_ABI_VERSION:

@@ -196,3 +196,33 @@ def test_optimizer_steps_reduce_loss():
         model.w_fin.bias.add_(0.5)
         e2 = model(x)
     assert torch.allclose(e2[:, :8], e1[:, :8] + 0.5, atol=1e-5)
+
+
+def test_fused_clip_adam_matches_torch():
+    """FusedClipAdam == clip_grad_norm_(model.parameters(), 3) + torch.optim.Adam.step() (+ StepLR), trainer.py:159-161,
+    including a loss-side parameter (AutoTune log_sigmas) that is optimised but not clipped."""
+    from monoloco_b200.train import FusedClipAdam
+    from monoloco_b200 import _lib as L_
+    torch.manual_seed(0)
+    shapes = [(1024, 34), (1024,), (1024, 1024), (8, 1024), (1,), (7,)]
+    ref = [torch.randn(s, device='cuda').requires_grad_(True) for s in shapes]
+    mine = [t.detach().clone().requires_grad_(True) for t in ref]
+    o_ref = torch.optim.Adam(ref, lr=2e-3)
+    o_mine = FusedClipAdam(mine, lr=2e-3, max_norm=3.0, clip_params=mine[:-1])
+    s_ref = torch.optim.lr_scheduler.StepLR(o_ref, step_size=2, gamma=0.5)
+    s_mine = torch.optim.lr_scheduler.StepLR(o_mine, step_size=2, gamma=0.5)
+    for it in range(5):
+        scale = 10.0 if it % 2 == 0 else 0.01  # clipping active / inactive
+        for a, b in zip(ref, mine):
+            g = torch.randn_like(a) * scale
+            a.grad, b.grad = g.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_(ref[:-1], 3)
+        o_ref.step()
+        s_ref.step()
+        n0 = L_.lib().mlb_launch_count()
+        v0 = mine[0]._version
+        o_mine.step()
+        s_mine.step()
+        assert L_.lib().mlb_launch_count() - n0 == 2 and mine[0]._version == v0 + 1
+        for a, b in zip(ref, mine):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
