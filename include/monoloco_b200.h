@@ -179,7 +179,8 @@ typedef struct mlb_train_args {
     int32_t aux_block;             /* block whose output feeds w_aux (LocoModel.w2); w_fin reads the last block */
     int32_t update_running_stats;  /* 1 in training (nn.BatchNorm1d momentum update, unbiased variance)         */
     int32_t rows_per_group;        /* 0 = auto                                                                  */
-    float p_dropout, bn_eps, bn_momentum, reserved0;
+    float p_dropout, bn_eps, bn_momentum;
+    int32_t flags;                 /* reserved, must be 0                                                       */
     uint64_t drop_seed;            /* counter-RNG seed (must be the same in forward and backward)               */
     const uint8_t* drop_mask;      /* optional explicit keep masks [n_bn_blocks][B][L] (parity tests)           */
     const float* x;                /* [B, input_size] pre-processed inputs                                      */
@@ -205,6 +206,10 @@ int mlb_train_step(mlb_train_handle h, const mlb_train_args* a, const mlb_train_
 /* profiling aid: wall time (ns) of every phase of the most recent launch (synchronises the device);
  * returns the number of phases written. types: 0 PACK, 1 FWD, 2 FWD_FINAL, 3 BWD_INIT, 4 BWD_HEAD, 5 BWD, 6 DW. */
 int mlb_train_phase_times(mlb_train_handle h, int max_n, double* out_ns, int* types, int* blks);
+/* profiling aid: out_ns[(ph*3 + s)*8 + k] = ns since the start of phase ph at which CTA s (0 first, 1 middle, 2 last
+ * active) passed point k (0 input tile ready, 1 GEMM done, 2 epilogue done, 3 left the grid barrier,
+ * 4 batch statistics loaded, 5 tile rows finished, 6-7 spare); 0 where unset. */
+int mlb_train_subphase_times(mlb_train_handle h, int max_n, double* out_ns);
 
 /* ---- optimizer side of the train step (trainer.py:159-160): clip_grad_norm_(params, max_norm) + Adam.step() over a
  * list of fp32 tensors (device pointers, host arrays of pointers / sizes), two multi-tensor launches, no host sync.

@@ -19,7 +19,8 @@ FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, F
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
-           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_adam_clip_step',
+           'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
+           'mlb_adam_clip_step',
            'mlb_probe_ffma',
            'mlb_launch_count']
 
@@ -59,7 +60,7 @@ class MlbTrainArgs(C.Structure):
     _fields_ = [('n_rows', C.c_int32), ('input_size', C.c_int32), ('output_size', C.c_int32), ('linear_size', C.c_int32),
                 ('n_blocks', C.c_int32), ('aux_block', C.c_int32), ('update_running_stats', C.c_int32),
                 ('rows_per_group', C.c_int32),
-                ('p_dropout', C.c_float), ('bn_eps', C.c_float), ('bn_momentum', C.c_float), ('reserved0', C.c_float),
+                ('p_dropout', C.c_float), ('bn_eps', C.c_float), ('bn_momentum', C.c_float), ('flags', C.c_int32),
                 ('drop_seed', C.c_uint64), ('drop_mask', C.c_void_p), ('x', C.c_void_p), ('out', C.c_void_p),
                 ('g_out', C.c_void_p),
                 ('W_aux', C.c_void_p), ('b_aux', C.c_void_p), ('W_fin', C.c_void_p), ('b_fin', C.c_void_p),
@@ -104,6 +105,7 @@ def lib():
     for fn in (l.mlb_train_forward, l.mlb_train_backward, l.mlb_train_step):
         fn.argtypes = [C.c_void_p, C.POINTER(MlbTrainArgs), C.POINTER(MlbTrainBlock), C.c_void_p]
     l.mlb_train_phase_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.mlb_train_subphase_times.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     l.mlb_adam_clip_step.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
                                      C.c_void_p, C.c_void_p]

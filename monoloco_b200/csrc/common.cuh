@@ -146,10 +146,20 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
 __device__ __forceinline__ uint32_t mix32(uint64_t x) {  // 64-bit counter -> 32 random bits (Laplace sampler)
     return fmix32((uint32_t)x ^ fmix32((uint32_t)(x >> 32) + 0x9E3779B9u));
 }
+// Dropout keep decision for element (site, row, col): r = fmix32(S ^ row*K ^ fmix32(col, site)), keep iff the top 24 bits
+// as a fraction are >= p.  Split so that callers hoist the per-column / per-row / per-launch parts out of their loops.
+__device__ __forceinline__ uint32_t drop_seed_mix(uint64_t seed) { return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u); }
+__device__ __forceinline__ uint32_t drop_col_hash(uint32_t col, uint32_t site) {
+    return fmix32(col * 0x85EBCA77u + site * 0xC2B2AE3Du + 0x27D4EB2Fu);
+}
+__device__ __forceinline__ uint32_t drop_row_mix(uint32_t seed_mix, uint32_t row) { return seed_mix ^ (row * 0x9E3779B1u); }
+// (float)(r >> 8) * 2^-24 >= p  <=>  (r >> 8) >= ceil(p * 2^24)   (both sides exact)
+__device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)ceilf(p * 16777216.0f); }
+__device__ __forceinline__ bool drop_keep(uint32_t row_mix, uint32_t col_hash, uint32_t thr) {
+    return (fmix32(row_mix ^ col_hash) >> 8) >= thr;
+}
 __device__ __forceinline__ bool keep_draw(uint64_t seed, uint32_t site, uint32_t row, uint32_t col, float p) {
-    const uint32_t s = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
-    const uint32_t r = fmix32(s ^ (row * 0x9E3779B1u) ^ fmix32(col * 0x85EBCA77u + site * 0xC2B2AE3Du + 0x27D4EB2Fu));
-    return (float)(r >> 8) * (1.0f / 16777216.0f) >= p;
+    return drop_keep(drop_row_mix(drop_seed_mix(seed), row), drop_col_hash(col, site), drop_threshold(p));
 }
 
 }  // namespace mlb

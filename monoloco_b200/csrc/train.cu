@@ -79,6 +79,50 @@ __device__ __forceinline__ bool keep_elem(const TrainParams& p, int site, int gr
     if (p.drop_mask != nullptr) return p.drop_mask[((size_t)site * p.n_rows + grow) * p.L + col] != 0;
     return keep_draw(p.seed, (uint32_t)site, (uint32_t)grow, (uint32_t)col, p.p_drop);
 }
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t a) {
+    return ((a & 0xFFu) ? 1u : 0u) | ((a & 0xFF00u) ? 2u : 0u) | ((a & 0xFF0000u) ? 4u : 0u) | ((a & 0xFF000000u) ? 8u : 0u);
+}
+// Keep decisions of 8 elements of one row as a bit field (bit j <-> element j); ONE mask-vs-hash branch per row, the
+// per-launch (seed_mix, thr) and per-column (ch) parts of the hash hoisted by the caller.
+//   accumulator layout: columns n0..n0+3 and n0+64..n0+67
+__device__ __forceinline__ uint32_t keep_bits_acc(const TrainParams& p, int site, uint32_t seed_mix, uint32_t thr,
+                                                  const uint32_t (&ch)[8], size_t grow, int n0) {
+    if (p.p_drop <= 0.f) return 0xFFu;
+    if (p.drop_mask != nullptr) {
+        const uint8_t* m = p.drop_mask + ((size_t)site * p.n_rows + grow) * p.L + n0;
+        return bytes_to_bits(*reinterpret_cast<const uint32_t*>(m)) | (bytes_to_bits(*reinterpret_cast<const uint32_t*>(m + 64)) << 4);
+    }
+    const uint32_t rm = drop_row_mix(seed_mix, (uint32_t)grow);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bits |= (drop_keep(rm, ch[j], thr) ? 1u : 0u) << j;
+    return bits;
+}
+//   8 consecutive columns col0..col0+7 (col0 % 8 == 0)
+__device__ __forceinline__ uint32_t keep_bits_run(const TrainParams& p, int site, uint32_t seed_mix, uint32_t thr, size_t grow,
+                                                  int col0) {
+    if (p.p_drop <= 0.f) return 0xFFu;
+    if (p.drop_mask != nullptr) {
+        const uint8_t* m = p.drop_mask + ((size_t)site * p.n_rows + grow) * p.L + col0;
+        return bytes_to_bits(*reinterpret_cast<const uint32_t*>(m)) | (bytes_to_bits(*reinterpret_cast<const uint32_t*>(m + 4)) << 4);
+    }
+    const uint32_t rm = drop_row_mix(seed_mix, (uint32_t)grow);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bits |= (drop_keep(rm, drop_col_hash((uint32_t)(col0 + e), (uint32_t)site), thr) ? 1u : 0u) << e;
+    return bits;
+}
+
+// profiling aid: CTAs 0, grid/2 and n_tiles-1 stamp globaltimer at up to 4 points inside every phase
+__device__ __forceinline__ void mark(const TrainParams& p, int ph, int slot, int tid) {
+    if (tid != 0) return;
+    const int b = blockIdx.x;
+    const int sel = b == 0 ? 0 : (b == (int)gridDim.x / 2 ? 1 : (b == p.n_tiles - 1 ? 2 : -1));
+    if (sel < 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.phase_ns[MAX_PHASES + 1 + (ph * 3 + sel) * 8 + slot] = t;
+}
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* ptr) {
     unsigned v;
@@ -244,6 +288,78 @@ __device__ void head_forward(const float* __restrict__ W, const float* __restric
     }
 }
 
+// aux head (after LocoModel.w2) and, in the final phase, the w_fin head + fused MultiTaskLoss and its gradient g_out
+template <int TM>
+__device__ __forceinline__ void fwd_heads(const TrainParams& p, bool final_phase, int prev, const float* act, float* outs,
+                                          int row0, int rows_here, int tid, int warp, int lane, int nfin, float invB) {
+    const int L = p.L;
+    if (prev >= 0 && prev == p.aux_block) {  // w_aux head reads LocoModel.w2's output (architectures.py:60)
+        head_forward(p.W_aux, p.b_aux, 1, L, act, outs, nfin, warp, lane);
+        csync();
+        if (tid < MP) {
+            int rr;
+            if (slot_valid<TM>(tid, rows_here, rr)) p.out[(size_t)(row0 + rr) * p.out_size + nfin] = outs[tid * OUT_LD + nfin];
+        }
+    }
+    if (final_phase) {
+        head_forward(p.W_fin, p.b_fin, nfin, L, act, outs, 0, warp, lane);  // architectures.py:67
+        csync();
+        if (tid < MP) {
+            int rr;
+            const bool v = slot_valid<TM>(tid, rows_here, rr);
+            const size_t gr = (size_t)row0 + rr;
+            float lossv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (v) {
+                float* o = outs + tid * OUT_LD;
+                for (int k = 0; k < nfin; ++k) p.out[gr * p.out_size + k] = o[k];
+                if (p.labels != nullptr) {
+                    o[nfin] = p.out[gr * p.out_size + nfin];
+                    const float* y = p.labels + gr * p.label_ld;
+                    float gsum[OUT_LD];
+#pragma unroll
+                    for (int k = 0; k < OUT_LD; ++k) gsum[k] = 0.f;
+                    for (int t = 0; t < p.n_tasks; ++t) {
+                        const float s = p.task_scale[t] * invB;
+                        const int task = p.tasks[t];
+                        if (task == MLB_TASK_D) {  // LaplacianLoss, losses.py:121-131
+                            const float mu = o[2], si = o[3], xx = y[3];
+                            const float nrm = 1.f - mu / xx, e = expf(-si);
+                            lossv[t] = fabsf(nrm) * e + 0.01f + si + 2.f;
+                            const float sg = nrm > 0.f ? 1.f : (nrm < 0.f ? -1.f : 0.f);
+                            gsum[2] += s * sg * (-1.f / xx) * e;
+                            gsum[3] += s * (1.f - fabsf(nrm) * e);
+                        } else if (task == MLB_TASK_ORI) {  // nn.L1Loss over [B,2]
+                            const float d7 = o[7] - y[7], d8 = o[8] - y[8];
+                            lossv[t] = 0.5f * (fabsf(d7) + fabsf(d8));
+                            gsum[7] += 0.5f * s * (d7 > 0.f ? 1.f : (d7 < 0.f ? -1.f : 0.f));
+                            gsum[8] += 0.5f * s * (d8 > 0.f ? 1.f : (d8 < 0.f ? -1.f : 0.f));
+                        } else if (task == MLB_TASK_AUX) {  // nn.BCEWithLogitsLoss, label column 10
+                            const float zz = o[9], tt = y[10];
+                            lossv[t] = fmaxf(zz, 0.f) - zz * tt + log1pf(expf(-fabsf(zz)));
+                            gsum[9] += s * (1.f / (1.f + expf(-zz)) - tt);
+                        } else {  // nn.L1Loss on one column: x, y, h, w, l (process.py:252-254, 293-304)
+                            const int col = task == MLB_TASK_X ? 0 : task == MLB_TASK_Y ? 1 : task == MLB_TASK_H ? 4
+                                                                     : task == MLB_TASK_W ? 5 : 6;
+                            const float d = o[col] - y[col];
+                            lossv[t] = fabsf(d);
+                            gsum[col] += s * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+                        }
+                    }
+                    for (int k = 0; k < OUT_LD; ++k) p.g_out[gr * OUT_LD + k] = gsum[k];
+                }
+            }
+            if (p.labels != nullptr) {
+                for (int t = 0; t < p.n_tasks; ++t) {
+                    float v2 = lossv[t];
+                    for (int sft = 16; sft > 0; sft >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
+                    if (tid == 0) atomicAdd(&p.loss_acc[t], (double)v2);
+                }
+            }
+        }
+        csync();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int TM>
 __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid_constant__ TrainParams p) {
@@ -288,12 +404,26 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
     const float inv_keep = p.p_drop > 0.f ? 1.0f / (1.0f - p.p_drop) : 1.0f;
     const float invB = 1.0f / (float)p.n_rows;
     const int nfin = p.out_size - 1;
+    const uint32_t seed_mix = drop_seed_mix(p.seed), drop_thr = drop_threshold(p.p_drop);
+    auto col_hashes = [&](int site, uint32_t (&ch)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ch[j] = drop_col_hash((uint32_t)col_of(n0, j), (uint32_t)site);
+    };
 
     if (blockIdx.x == 0 && tid == 0) {
         unsigned long long t0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         p.phase_ns[0] = t0;
     }
+    auto end_phase = [&](int ph_done) {
+        grid_barrier(p, bar_target, released, tid);
+        mark(p, ph_done, 3, tid);
+        if (blockIdx.x == 0 && tid == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            p.phase_ns[ph_done + 1] = t1;
+        }
+    };
     for (int ph = 0; ph < p.n_phases; ++ph) {
         const int type = p.phase_type[ph], bi = p.phase_blk[ph];
 
@@ -380,12 +510,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                                     res[0] = r0.x, res[1] = r0.y, res[2] = r0.z, res[3] = r0.w;
                                     res[4] = r1.x, res[5] = r1.y, res[6] = r1.z, res[7] = r1.w;
                                 }
+                                const uint32_t kb = keep_bits_run(p, pb.bn_index, seed_mix, drop_thr, grow, k8 * 8);
 #pragma unroll
                                 for (int e = 0; e < 8; ++e) {
                                     const float4 t = pt[2 * (k8 * 8 + e)];  // mean, invstd, gamma, beta
                                     const float zh = (z[e] - t.x) * t.y;
                                     float y = fmaxf(fmaf(zh, t.z, t.w), 0.f);
-                                    y = keep_elem(p, pb.bn_index, (int)grow, k8 * 8 + e) ? y * inv_keep : 0.f;
+                                    y = (kb >> e) & 1u ? y * inv_keep : 0.f;
                                     h[e] = y + res[e];
                                 }
                                 float* dst = Ap + grow * L + k8 * 8;
@@ -409,72 +540,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                         for (int idx = tid; idx < (p.n_rows_pad - p.n_rows) * L; idx += NT) pb.Aout[(size_t)p.n_rows * L + idx] = 0.f;
                 }
                 csync();
-                if (prev >= 0 && prev == p.aux_block) {  // w_aux head reads LocoModel.w2's output (architectures.py:60)
-                    head_forward(p.W_aux, p.b_aux, 1, L, act, outs, nfin, warp, lane);
-                    csync();
-                    if (tid < MP) {
-                        int rr;
-                        if (slot_valid<TM>(tid, rows_here, rr)) p.out[(size_t)(row0 + rr) * p.out_size + nfin] = outs[tid * OUT_LD + nfin];
-                    }
-                }
-                if (final_phase) {
-                    head_forward(p.W_fin, p.b_fin, nfin, L, act, outs, 0, warp, lane);  // architectures.py:67
-                    csync();
-                    if (tid < MP) {
-                        int rr;
-                        const bool v = slot_valid<TM>(tid, rows_here, rr);
-                        const size_t gr = (size_t)row0 + rr;
-                        float lossv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        if (v) {
-                            float* o = outs + tid * OUT_LD;
-                            for (int k = 0; k < nfin; ++k) p.out[gr * p.out_size + k] = o[k];
-                            if (p.labels != nullptr) {
-                                o[nfin] = p.out[gr * p.out_size + nfin];
-                                const float* y = p.labels + gr * p.label_ld;
-                                float gsum[OUT_LD];
-#pragma unroll
-                                for (int k = 0; k < OUT_LD; ++k) gsum[k] = 0.f;
-                                for (int t = 0; t < p.n_tasks; ++t) {
-                                    const float s = p.task_scale[t] * invB;
-                                    const int task = p.tasks[t];
-                                    if (task == MLB_TASK_D) {  // LaplacianLoss, losses.py:121-131
-                                        const float mu = o[2], si = o[3], xx = y[3];
-                                        const float nrm = 1.f - mu / xx, e = expf(-si);
-                                        lossv[t] = fabsf(nrm) * e + 0.01f + si + 2.f;
-                                        const float sg = nrm > 0.f ? 1.f : (nrm < 0.f ? -1.f : 0.f);
-                                        gsum[2] += s * sg * (-1.f / xx) * e;
-                                        gsum[3] += s * (1.f - fabsf(nrm) * e);
-                                    } else if (task == MLB_TASK_ORI) {  // nn.L1Loss over [B,2]
-                                        const float d7 = o[7] - y[7], d8 = o[8] - y[8];
-                                        lossv[t] = 0.5f * (fabsf(d7) + fabsf(d8));
-                                        gsum[7] += 0.5f * s * (d7 > 0.f ? 1.f : (d7 < 0.f ? -1.f : 0.f));
-                                        gsum[8] += 0.5f * s * (d8 > 0.f ? 1.f : (d8 < 0.f ? -1.f : 0.f));
-                                    } else if (task == MLB_TASK_AUX) {  // nn.BCEWithLogitsLoss, label column 10
-                                        const float zz = o[9], tt = y[10];
-                                        lossv[t] = fmaxf(zz, 0.f) - zz * tt + log1pf(expf(-fabsf(zz)));
-                                        gsum[9] += s * (1.f / (1.f + expf(-zz)) - tt);
-                                    } else {  // nn.L1Loss on one column: x, y, h, w, l (process.py:252-254, 293-304)
-                                        const int col = task == MLB_TASK_X ? 0 : task == MLB_TASK_Y ? 1 : task == MLB_TASK_H ? 4
-                                                                                 : task == MLB_TASK_W ? 5 : 6;
-                                        const float d = o[col] - y[col];
-                                        lossv[t] = fabsf(d);
-                                        gsum[col] += s * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-                                    }
-                                }
-                                for (int k = 0; k < OUT_LD; ++k) p.g_out[gr * OUT_LD + k] = gsum[k];
-                            }
-                        }
-                        if (p.labels != nullptr) {
-                            for (int t = 0; t < p.n_tasks; ++t) {
-                                float v2 = lossv[t];
-                                for (int sft = 16; sft > 0; sft >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, sft);
-                                if (tid == 0) atomicAdd(&p.loss_acc[t], (double)v2);
-                            }
-                        }
-                    }
-                    csync();
-                    continue;
-                }
+                mark(p, ph, 0, tid);
+                fwd_heads<TM>(p, final_phase, prev, act, outs, row0, rows_here, tid, warp, lane, nfin, invB);
+                if (final_phase) continue;
                 // ---- GEMM + epilogue of block bi
                 const TBlk& b = p.blk[bi];
                 if (gemm_warp) {
@@ -482,6 +550,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     acc_zero<TM>(acc2);
                     tile_gemm<TM>(acc2, b.Kpad / KC, [&](int ch, unsigned) { return act + (size_t)ch * KC * MP; }, ring, full,
                                   empty, rs, n0, g, lane, L, p.err_flag);
+                    mark(p, ph, 1, tid);
                     float acc[TM][8];
                     acc_unpack<TM>(acc2, acc);
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(b.b + n0));
@@ -521,6 +590,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     }
                 }
                 csync();
+                mark(p, ph, 2, tid);
             }
         } else if (type == PH_BWD_HEAD) {
             // ============================================================================ head backward
@@ -630,6 +700,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                         const float4 g1 = *reinterpret_cast<const float4*>(Gp + grow * L + k8 * 8 + 4);
                         const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
                         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                        const uint32_t kb = keep_bits_run(p, b.bn_index, seed_mix, drop_thr, grow, k8 * 8);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
                             const float4 t = pt[2 * (k8 * 8 + e)];
@@ -637,7 +708,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                             const float zh = (z[e] - t.x) * t.y;
                             const float y = fmaf(zh, t.z, t.w);
                             float gy = y > 0.f ? gg[e] : 0.f;
-                            gy = keep_elem(p, b.bn_index, (int)grow, k8 * 8 + e) ? gy * inv_keep : 0.f;
+                            gy = (kb >> e) & 1u ? gy * inv_keep : 0.f;
                             gz[e] = t.z * t.y * (gy - u.x - zh * u.y);
                         }
                         float* dst = Gzp + grow * L + k8 * 8;
@@ -655,6 +726,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 if (tile == p.n_tiles - 1)
                     for (int idx = tid; idx < (p.n_rows_pad - p.n_rows) * L; idx += NT) b.Gz[(size_t)p.n_rows * L + idx] = 0.f;
                 csync();
+                mark(p, ph, 0, tid);
                 if (bi == 0) {
                     // first layer: dW0[n][k] = sum_rows gz[row][n] * x[row][k]  (K = 34 | 68), no dX needed.
                     // thread <-> feature n (coalesced re-read of the Gz rows just written), x tile broadcast from smem
@@ -685,9 +757,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                         acc_zero<TM>(acc2);
                         tile_gemm<TM>(acc2, L / KC, [&](int ch, unsigned) { return act + (size_t)ch * KC * MP; }, ring, full, empty,
                                       rs, n0, g, lane, L, p.err_flag);
+                        mark(p, ph, 1, tid);
                         float acc[TM][8];
                         acc_unpack<TM>(acc2, acc);
                         float wa[8], mean[8], invstd[8], gam[8], bet[8];
+                        uint32_t ch[8];
+                        col_hashes(pb.has_bn ? pb.bn_index : 0, ch);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int col = col_of(n0, j);
@@ -703,6 +778,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                             }
                         }
                         float s3[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        // __restrict__ views (distinct workspace buffers): the loads of later rows may pass the stores of earlier ones
+                        const float* __restrict__ SKp = pb.skip_to >= 0 ? p.blk[pb.skip_to].G : nullptr;
+                        const float* __restrict__ Zq = pb.Z;
+                        const float* __restrict__ gsr = gsrc;
+                        float* __restrict__ Gq = pb.G;
+                        float* __restrict__ Gzq = pb.Gz;
 #pragma unroll
                         for (int i = 0; i < TM; ++i) {
                             const int rr = g * TM + i;
@@ -712,30 +793,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) G[j] = acc[i][j];
                                 if (pb.skip_to >= 0) {  // x + y of MyLinearSimple: the skip path's gradient (architectures.py:100)
-                                    const float* sk = p.blk[pb.skip_to].G + gr * L + n0;
+                                    const float* sk = SKp + gr * L + n0;
                                     const float4 k0 = *reinterpret_cast<const float4*>(sk);
                                     const float4 k1 = *reinterpret_cast<const float4*>(sk + 64);
                                     G[0] += k0.x, G[1] += k0.y, G[2] += k0.z, G[3] += k0.w;
                                     G[4] += k1.x, G[5] += k1.y, G[6] += k1.z, G[7] += k1.w;
                                 }
                                 if (cur - 1 == p.aux_block) {
-                                    const float ga = gsrc[gr * gld + nfin];
+                                    const float ga = gsr[gr * gld + nfin];
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) G[j] = fmaf(ga, wa[j], G[j]);
                                 }
-                                float* dst = pb.G + gr * L + n0;
+                                float* dst = Gq + gr * L + n0;
                                 *reinterpret_cast<float4*>(dst) = make_float4(G[0], G[1], G[2], G[3]);
                                 *reinterpret_cast<float4*>(dst + 64) = make_float4(G[4], G[5], G[6], G[7]);
                                 if (pb.has_bn) {
-                                    const float4 z0 = *reinterpret_cast<const float4*>(pb.Z + gr * L + n0);
-                                    const float4 z1 = *reinterpret_cast<const float4*>(pb.Z + gr * L + n0 + 64);
+                                    const float4 z0 = *reinterpret_cast<const float4*>(Zq + gr * L + n0);
+                                    const float4 z1 = *reinterpret_cast<const float4*>(Zq + gr * L + n0 + 64);
                                     const float z[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                                    const uint32_t kb = keep_bits_acc(p, pb.bn_index, seed_mix, drop_thr, ch, gr, n0);
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) {
                                         const float zh = (z[j] - mean[j]) * invstd[j];
                                         const float y = fmaf(zh, gam[j], bet[j]);
                                         float gy = y > 0.f ? G[j] : 0.f;
-                                        gy = keep_elem(p, pb.bn_index, (int)gr, col_of(n0, j)) ? gy * inv_keep : 0.f;
+                                        gy = (kb >> j) & 1u ? gy * inv_keep : 0.f;
                                         s3[j] += gy;
                                         s4[j] = fmaf(gy, zh, s4[j]);
                                     }
@@ -745,7 +827,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                                         acc[i][j] = G[j];  // no BatchNorm below (LocoModel.w2): gz == G, chained as the next A tile
                                         s3[j] += G[j];
                                     }
-                                    float* dz = pb.Gz + gr * L + n0;
+                                    float* dz = Gzq + gr * L + n0;
                                     *reinterpret_cast<float4*>(dz) = make_float4(G[0], G[1], G[2], G[3]);
                                     *reinterpret_cast<float4*>(dz + 64) = make_float4(G[4], G[5], G[6], G[7]);
                                 }
@@ -791,6 +873,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                     }
                     csync();
                 }
+                mark(p, ph, 2, tid);
             }
         } else if (type == PH_DW) {
             // ============================================================================ weight gradients
@@ -834,12 +917,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_train_kernel(const __grid
                 u += c1 - c0;
             }
         }
-        grid_barrier(p, bar_target, released, tid);
-        if (blockIdx.x == 0 && tid == 0) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            p.phase_ns[ph + 1] = t1;
-        }
+        end_phase(ph);
     }
     // ---- finalise: per-task loss means (losses.py:139 torch.mean)
     if (blockIdx.x == 0 && p.labels != nullptr && tid < p.n_tasks) p.loss_vals[tid] = (float)(p.loss_acc[tid] / (double)p.n_rows);
@@ -918,7 +996,8 @@ extern "C" int mlb_train_create(int device, int max_rows, int input_size, int li
     TCU(cudaMalloc(&t->bar, sizeof(unsigned)));
     TCU(cudaMalloc(&t->err, sizeof(int)));
     TCU(cudaMemset(t->err, 0, sizeof(int)));
-    TCU(cudaMalloc(&t->phase_ns, (MAX_PHASES + 1) * sizeof(unsigned long long)));
+    TCU(cudaMalloc(&t->phase_ns, (MAX_PHASES + 1 + MAX_PHASES * 24) * sizeof(unsigned long long)));
+    TCU(cudaMemset(t->phase_ns, 0, (MAX_PHASES + 1 + MAX_PHASES * 24) * sizeof(unsigned long long)));
     *out = t;
     return 0;
 }
@@ -1066,6 +1145,23 @@ extern "C" int mlb_train_phase_times(mlb_train_handle t, int max_n, double* out_
         if (types) types[i] = t->last_phase_type[i];
         if (blks) blks[i] = t->last_phase_blk[i];
     }
+    return n;
+}
+
+// profiling aid: out_ns[(ph*3 + s)*8 + k] = time since the start of phase ph at which CTA s (0: first, 1: middle, 2: last
+// active) passed point k (0: input tile ready, 1: GEMM done, 2: epilogue done, 3: left the grid barrier, 4 batch statistics loaded, 5 tile rows finished, 6-7 spare); 0 where unset.
+extern "C" int mlb_train_subphase_times(mlb_train_handle t, int max_n, double* out_ns) {
+    if (!t || !out_ns) return tfail("mlb_train_subphase_times: bad argument");
+    TCU(cudaSetDevice(t->device));
+    TCU(cudaDeviceSynchronize());
+    static unsigned long long ts[MAX_PHASES + 1 + MAX_PHASES * 24];
+    TCU(cudaMemcpy(ts, t->phase_ns, sizeof(ts), cudaMemcpyDeviceToHost));
+    int n = t->last_n_phases < max_n ? t->last_n_phases : max_n;
+    for (int i = 0; i < n; ++i)
+        for (int q = 0; q < 24; ++q) {
+            const unsigned long long v = ts[MAX_PHASES + 1 + i * 24 + q];
+            out_ns[i * 24 + q] = v > ts[i] ? (double)(v - ts[i]) : 0.0;
+        }
     return n;
 }
 

@@ -210,3 +210,13 @@ def phase_times(model):
     bk = (C.c_int * 64)()
     n = ws.lib.mlb_train_phase_times(ws.h, 64, ns, ty, bk)
     return [(names[ty[i]], bk[i], ns[i] * 1e-6) for i in range(n)]
+
+
+def subphase_times(model):
+    """[(phase name, block, [[ms at point k for k in 0..7] for CTA first/middle/last])] of the most recent train launch:
+    points are 0 input tile ready, 1 GEMM done, 2 epilogue done, 3 left the grid barrier, 4 statistics loaded, 5 tile rows finished (profiling aid)."""
+    ws = _WS.get(model)
+    ph = phase_times(model)
+    ns = (C.c_double * (64 * 24))()
+    n = ws.lib.mlb_train_subphase_times(ws.h, 64, ns)
+    return [(ph[i][0], ph[i][1], [[ns[i * 24 + s * 8 + k] * 1e-6 for k in range(8)] for s in range(3)]) for i in range(n)]

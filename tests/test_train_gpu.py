@@ -114,11 +114,16 @@ def _cmp_grad_statistical(name, got, ref):
         assert np.abs(got - ref).max() <= 2e-5 * scale + 2e-7, name
 
 
-@pytest.mark.parametrize('tm', [10, 12, 14, 16])
+@pytest.mark.parametrize('tm', [8, 10, 12, 14, 16])
 def test_train_tile_shapes(tm, monkeypatch):
     """Every rows-per-group instantiation of the train kernel (ragged last tile, padded DW tail) -- tight rule."""
     monkeypatch.setenv('MLB_TRAIN_ROWS_PER_GROUP', str(tm))
     test_train_step_vs_torch_autograd(256, 2, 301, 0.2)
+
+
+def test_train_two_tiles_per_cta():
+    """More row tiles than SMs (batch 6000 -> CTAs walk two tiles per phase)."""
+    test_train_step_vs_torch_autograd(1024, 3, 6000, 0.2)
 
 
 @pytest.mark.parametrize('L,st,B,p', [(256, 3, 301, 0.2), (1024, 3, 4096, 0.2), (1024, 1, 29, 0.0), (512, 3, 1000, 0.5)])

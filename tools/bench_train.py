@@ -25,7 +25,8 @@ def timeit(fn, n=10, warm=3):
 
 for B in [int(v) for v in (sys.argv[1:] or ['4096', '512'])]:
     sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 7)
-    m = LocoModel(34, 9, 1024, p_dropout=0.2, num_stage=3)
+    PD = float(os.environ.get('MLB_BENCH_PDROP', '0.2'))
+    m = LocoModel(34, 9, 1024, p_dropout=PD, num_stage=3)
     m.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in sd.items()})
     m.cuda().train()
     x = torch.from_numpy(synthetic.make_inputs(B, 34, seed=3)).cuda()
@@ -34,6 +35,12 @@ for B in [int(v) for v in (sys.argv[1:] or ['4096', '512'])]:
     t_fused = timeit(lambda: train_step(m, x, y, tasks))
     from monoloco_b200.train.fused import phase_times
     print('   phases (ms):', ' '.join('%s%d:%.3f' % (n, b, ms) for n, b, ms in phase_times(m)))
+    if os.environ.get('MLB_SUBPHASES'):
+        from monoloco_b200.train.fused import subphase_times
+        for n, b, pts in subphase_times(m):
+            if n in ('FWD', 'BWD', 'FWD_FINAL'):
+                # CTA first | last: stats loaded, rows finished, act written, tile ready, GEMM done, epilogue done, barrier left
+                print('   %-9s %d  ' % (n, b) + ' | '.join(' '.join('%.3f' % pts[c][k] for k in (4, 5, 6, 0, 1, 2, 3)) for c in (0, 2)))
 
     def dropin():
         m.zero_grad(set_to_none=True)
@@ -47,7 +54,7 @@ for B in [int(v) for v in (sys.argv[1:] or ['4096', '512'])]:
     def eager():
         for v in tsd.values():
             v.grad = None
-        out = T.model_forward(tsd, x, training=True, p_dropout=0.2)
+        out = T.model_forward(tsd, x, training=True, p_dropout=PD)
         loss, _ = T.multi_task_loss(out, y, tasks)
         loss.backward()
     t_eager = timeit(eager)
