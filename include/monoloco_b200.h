@@ -194,6 +194,8 @@ typedef struct mlb_train_args {
     int32_t tasks[8];              /* MLB_TASK_*                                                                */
     float task_scale[8];           /* lambda_t (MultiTaskLoss) or lambda_t / (2 exp(log_sigma_t)^2) (AutoTune)  */
     float* loss_vals;              /* [8] unweighted per-task means (device)                                    */
+    const float* task_scale_dev;   /* optional device copy of task_scale[] (overrides it): lets AutoTune's       */
+                                   /* lambda_t / (2 exp(log_sigma_t)^2) stay on the device, no host sync         */
 } mlb_train_args;
 
 typedef struct mlb_train* mlb_train_handle;
@@ -237,6 +239,10 @@ int mlb_probe_ffma(int device, int blocks, int iters, double* flops, void* strea
 
 /* number of kernels this library has launched in this process (bench.py "gpu_launches") */
 uint64_t mlb_launch_count(void);
+/* profiling aid: point the tile kernel's timestamp marks at a device buffer of >= 4*n_ops + 4 uint64 (NULL: off, the
+ * default).  CTA 0 stamps %globaltimer at: [0] start, [1] input tile staged, per op i [2+4i] GEMM done, [3+4i] epilogue
+ * math done, [4+4i] CTA synchronised, [5+4i] activation tile rewritten; [2+4n] heads done, [3+4n] rows stored. */
+int mlb_debug_fwd_marks(void* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 
            'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
            'mlb_adam_clip_step',
            'mlb_probe_ffma',
-           'mlb_launch_count']
+           'mlb_launch_count', 'mlb_debug_fwd_marks']
 
 
 class MlbOp(C.Structure):
@@ -66,7 +66,8 @@ class MlbTrainArgs(C.Structure):
                 ('W_aux', C.c_void_p), ('b_aux', C.c_void_p), ('W_fin', C.c_void_p), ('b_fin', C.c_void_p),
                 ('dW_aux', C.c_void_p), ('db_aux', C.c_void_p), ('dW_fin', C.c_void_p), ('db_fin', C.c_void_p),
                 ('labels', C.c_void_p), ('label_ld', C.c_int32), ('n_tasks', C.c_int32),
-                ('tasks', C.c_int32 * 8), ('task_scale', C.c_float * 8), ('loss_vals', C.c_void_p)]
+                ('tasks', C.c_int32 * 8), ('task_scale', C.c_float * 8), ('loss_vals', C.c_void_p),
+                ('task_scale_dev', C.c_void_p)]
 
 
 _lib = None

@@ -158,6 +158,10 @@ __device__ __forceinline__ uint32_t drop_threshold(float p) { return (uint32_t)c
 __device__ __forceinline__ bool drop_keep(uint32_t row_mix, uint32_t col_hash, uint32_t thr) {
     return (fmix32(row_mix ^ col_hash) >> 8) >= thr;
 }
+// 4 mask bytes (little endian) -> 4 keep bits
+__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t a) {
+    return ((a & 0xFFu) ? 1u : 0u) | ((a & 0xFF00u) ? 2u : 0u) | ((a & 0xFF0000u) ? 4u : 0u) | ((a & 0xFF000000u) ? 8u : 0u);
+}
 __device__ __forceinline__ bool keep_draw(uint64_t seed, uint32_t site, uint32_t row, uint32_t col, float p) {
     return drop_keep(drop_row_mix(drop_seed_mix(seed), row), drop_col_hash(col, site), drop_threshold(p));
 }

@@ -74,6 +74,16 @@ __device__ __forceinline__ void producer_loop(const FwdParams& p, float* ring, u
     }
 }
 
+// profiling aid (mlb_debug_fwd_marks): when set, thread 0 of CTA 0 stamps globaltimer at points of the layer program
+__device__ unsigned long long* g_fwd_marks = nullptr;
+__device__ __forceinline__ void fmark(unsigned long long* marks, int slot) {
+    if (marks != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        marks[slot] = t;
+    }
+}
+
 template <int TM>
 __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -135,6 +145,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
         const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
         // this thread's 8 output columns: n0 + {0..3} and n0 + 64 + {0..3}
         const int n0 = warp * 128 + c * 4;
+        unsigned long long* marks = (tid == 0 && blockIdx.x == 0) ? g_fwd_marks : nullptr;
+        fmark(marks, 0);
 
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int row0 = tile * ROWS;
@@ -208,6 +220,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 }
             }
 
+            fmark(marks, 1);
             // ---------------------------------------------------------------- layer program
             int site = 0;
             for (int oi = 0; oi < p.n_ops; ++oi) {
@@ -260,6 +273,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                         if (!next_ready) mbar_wait(&full[nstage], nparity, p.err_flag);
                         stage = nstage, parity = nparity;
                     }
+                    fmark(marks, 2 + 4 * oi);
                     float acc[TM][8];
 #pragma unroll
                     for (int i = 0; i < TM / 2; ++i)
@@ -287,20 +301,30 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                     }
                     if (op.flags & MLB_F_DROPOUT) {
                         if (p.flags & MLB_FWD_DROPOUT) {
+                            // one mask-vs-hash branch per row; per-launch / per-column parts of the hash hoisted (common.cuh)
                             const float inv_keep = 1.0f / (1.0f - p.p_drop);
+                            const uint32_t seed_mix = drop_seed_mix(p.drop_seed), thr = drop_threshold(p.p_drop);
+                            uint32_t ch[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) ch[j] = drop_col_hash((uint32_t)(n0 + (j & 3) + (j >> 2) * 64), (uint32_t)site);
 #pragma unroll
                             for (int i = 0; i < TM; ++i) {
                                 const int grow = row0 + g * TM + i;
+                                uint32_t kb = 0xFFu;
+                                if (p.drop_mask != nullptr) {
+                                    if (grow < p.n_rows) {
+                                        const uint8_t* m = p.drop_mask + ((size_t)site * p.n_rows + grow) * L + n0;
+                                        kb = bytes_to_bits(*reinterpret_cast<const uint32_t*>(m)) |
+                                             (bytes_to_bits(*reinterpret_cast<const uint32_t*>(m + 64)) << 4);
+                                    }
+                                } else {
+                                    const uint32_t rm = drop_row_mix(seed_mix, (uint32_t)grow);
+                                    kb = 0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const int n = n0 + (j & 3) + (j >> 2) * 64;
-                                    bool keep;
-                                    if (p.drop_mask != nullptr)
-                                        keep = grow < p.n_rows ? p.drop_mask[((size_t)site * p.n_rows + grow) * L + n] != 0 : true;
-                                    else
-                                        keep = keep_draw(p.drop_seed, site, grow, n, p.p_drop);
-                                    acc[i][j] = keep ? acc[i][j] * inv_keep : 0.f;
+                                    for (int j = 0; j < 8; ++j) kb |= (drop_keep(rm, ch[j], thr) ? 1u : 0u) << j;
                                 }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) acc[i][j] = (kb >> j) & 1u ? acc[i][j] * inv_keep : 0.f;
                             }
                         }
                         site++;
@@ -335,7 +359,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                                 for (int j = 0; j < 8; ++j) rs[(i * 8 + j) * RES_STRIDE] = acc[i][j];
                         }
                     }
+                    fmark(marks, 3 + 4 * oi);
                     consumer_sync(nthreads);  // every warp has finished reading `act` as this layer's input
+                    fmark(marks, 4 + 4 * oi);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float* dst = act + (size_t)(n0 + (j & 3) + (j >> 2) * 64) * MP + g * 16;
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                             *reinterpret_cast<float4*>(dst + v * 4) = t;
                         }
                     }
+                    fmark(marks, 5 + 4 * oi);
                     consumer_sync(nthreads);
                 } else {
                     // ---- narrow head: one warp per output column, lane = tile row slot
@@ -368,6 +395,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 }
             }
             consumer_sync(nthreads);
+            fmark(marks, 2 + 4 * p.n_ops);
 
             // ---------------------------------------------------------------- decode + store (one thread per row)
             if (tid < MP) {
@@ -406,6 +434,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 }
             }
             consumer_sync(nthreads);
+            fmark(marks, 3 + 4 * p.n_ops);
         }
         }  // active consumer warp
     }
@@ -635,6 +664,19 @@ static int fail(const std::string& msg) {
 extern "C" const char* mlb_last_error(void) { return g_err.c_str(); }
 extern "C" int mlb_abi_version(void) { return MLB_ABI_VERSION; }
 extern "C" uint64_t mlb_launch_count(void) { return g_launches.load(); }
+
+// profiling aid: point the tile kernel's timestamp marks at a device buffer of >= 4 * n_ops + 4 uint64 (nullptr: off).
+// CTA 0 stamps: [0] start, [1] input tile staged, per op i [2+4i] GEMM done, [3+4i] epilogue math done, [4+4i] CTA
+// synchronised, [5+4i] activation tile rewritten; [2+4n] heads done, [3+4n] rows stored.
+extern "C" int mlb_debug_fwd_marks(void* dev_buf) {
+    unsigned long long* ptr = reinterpret_cast<unsigned long long*>(dev_buf);
+    cudaError_t e = cudaMemcpyToSymbol(mlb::g_fwd_marks, &ptr, sizeof(ptr));
+    if (e != cudaSuccess) {
+        g_mlb_err = std::string("mlb_debug_fwd_marks: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    return 0;
+}
 extern "C" int mlb_num_sms(mlb_handle h) { return h ? h->n_sms : 0; }
 
 static size_t fwd_smem_bytes(int L) {

@@ -66,6 +66,7 @@ struct TrainParams {
     int label_ld, n_tasks;
     int tasks[8];
     float task_scale[8];
+    const float* task_scale_dev;  // optional device copy (overrides task_scale)
     float* loss_vals;
     double* loss_acc;  // [8]
     float4* ptab;      // [grid][L][2]
@@ -78,9 +79,6 @@ __device__ __forceinline__ bool keep_elem(const TrainParams& p, int site, int gr
     if (p.p_drop <= 0.f) return true;
     if (p.drop_mask != nullptr) return p.drop_mask[((size_t)site * p.n_rows + grow) * p.L + col] != 0;
     return keep_draw(p.seed, (uint32_t)site, (uint32_t)grow, (uint32_t)col, p.p_drop);
-}
-__device__ __forceinline__ uint32_t bytes_to_bits(uint32_t a) {
-    return ((a & 0xFFu) ? 1u : 0u) | ((a & 0xFF00u) ? 2u : 0u) | ((a & 0xFF0000u) ? 4u : 0u) | ((a & 0xFF000000u) ? 8u : 0u);
 }
 // Keep decisions of 8 elements of one row as a bit field (bit j <-> element j); ONE mask-vs-hash branch per row, the
 // per-launch (seed_mix, thr) and per-column (ch) parts of the hash hoisted by the caller.
@@ -319,7 +317,7 @@ __device__ __forceinline__ void fwd_heads(const TrainParams& p, bool final_phase
 #pragma unroll
                     for (int k = 0; k < OUT_LD; ++k) gsum[k] = 0.f;
                     for (int t = 0; t < p.n_tasks; ++t) {
-                        const float s = p.task_scale[t] * invB;
+                        const float s = (p.task_scale_dev != nullptr ? p.task_scale_dev[t] : p.task_scale[t]) * invB;
                         const int task = p.tasks[t];
                         if (task == MLB_TASK_D) {  // LaplacianLoss, losses.py:121-131
                             const float mu = o[2], si = o[3], xx = y[3];
@@ -1092,6 +1090,7 @@ static int train_launch(mlb_train_handle t, const mlb_train_args* a, const mlb_t
             p.tasks[i] = a->tasks[i], p.task_scale[i] = a->task_scale[i];
         }
         p.loss_vals = a->loss_vals;
+        p.task_scale_dev = a->task_scale_dev;
     }
     p.loss_acc = t->loss_acc, p.ptab = t->ptab, p.bar_counter = t->bar, p.err_flag = t->err;
     p.phase_ns = t->phase_ns;

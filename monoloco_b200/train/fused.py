@@ -39,6 +39,7 @@ class _Workspace:
         self.h = C.c_void_p()
         self.max_rows = max_rows
         self.blocks = _blocks_of(model)
+        self.lambda_cache = {}
         L_.check(self.lib.mlb_train_create(device.index if device.index is not None else torch.cuda.current_device(),
                                            max_rows, model.stereo_size, model.linear_size, len(self.blocks),
                                            C.byref(self.h)), 'mlb_train_create')
@@ -105,7 +106,11 @@ def _fill(model, ws, x, out, grads=None, g_out=None, labels=None, tasks=None, sc
         a.labels, a.label_ld, a.n_tasks = labels.data_ptr(), labels.shape[1], len(tasks)
         for i, t in enumerate(tasks):
             a.tasks[i] = L_.TASK_IDS[t]
-            a.task_scale[i] = float(scales[i])
+        if torch.is_tensor(scales):          # device tensor: the kernel reads it, nothing crosses to the host
+            a.task_scale_dev = scales.data_ptr()
+        else:
+            for i in range(len(tasks)):
+                a.task_scale[i] = float(scales[i])
         a.loss_vals = loss_vals.data_ptr()
     return a, blocks
 
@@ -125,9 +130,8 @@ def _check_model(model, x):
 
 
 def _bump_batches_tracked(model):
-    for m in model.modules():
-        if isinstance(m, torch.nn.BatchNorm1d):
-            m.num_batches_tracked += 1
+    # nn.BatchNorm1d.num_batches_tracked of every layer, one multi-tensor launch
+    torch._foreach_add_([m.num_batches_tracked for m in model.modules() if isinstance(m, torch.nn.BatchNorm1d)], 1)
 
 
 class _FusedTrainFn(torch.autograd.Function):
@@ -177,10 +181,15 @@ def train_step(model, x, labels, tasks, lambdas=None, log_sigmas=None, drop_mask
     x = x.detach().float().contiguous()
     labels = labels.detach().float().contiguous()
     out = torch.empty((x.shape[0], model.output_size + 1), dtype=torch.float32, device=x.device)
+    # task weights as a device tensor (cached per lambdas; AutoTune's depend on log_sigmas and are computed on the device):
+    # no host<->device synchronisation anywhere in the step, so consecutive steps queue back to back
+    lam = ws.lambda_cache.get(lambdas)
+    if lam is None:
+        lam = ws.lambda_cache[lambdas] = torch.tensor([float(v) for v in lambdas], dtype=torch.float32, device=x.device)
     if log_sigmas is not None:
-        scales = [lam / (2.0 * float(torch.exp(ls)) ** 2) for lam, ls in zip(lambdas, log_sigmas.detach())]
+        scales = lam / (2.0 * torch.exp(log_sigmas.detach().float()) ** 2)   # losses.py:36-38
     else:
-        scales = [float(lam) for lam in lambdas]
+        scales = lam
     grads = {n: torch.empty_like(p) for n, p in model.named_parameters()}
     loss_vals = torch.zeros(8, dtype=torch.float32, device=x.device)
     a, blocks = _fill(model, ws, x, out, grads=grads, labels=labels, tasks=tasks, scales=scales, loss_vals=loss_vals,
@@ -189,9 +198,7 @@ def train_step(model, x, labels, tasks, lambdas=None, log_sigmas=None, drop_mask
     _bump_batches_tracked(model)
     for n, p in model.named_parameters():
         p.grad = grads[n] if (p.grad is None or not accumulate) else p.grad + grads[n]
-    raw = loss_vals[:len(tasks)]
-    sc = torch.tensor(scales, dtype=torch.float32, device=x.device)
-    weighted = raw * sc
+    weighted = loss_vals[:len(tasks)] * scales
     loss = weighted.sum()
     if log_sigmas is not None:
         loss = loss + log_sigmas.detach().sum()

@@ -1,0 +1,33 @@
+"""Timeline of CTA 0 inside the tile forward kernel (mlb_debug_fwd_marks): per op GEMM / epilogue / sync / act-write us."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctypes as C
+import numpy as np, torch
+from monoloco_b200 import synthetic, _lib as L_
+from monoloco_b200.engine import LocoEngine
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+eng = LocoEngine(synthetic.make_state_dict('loco', 34, 9, 1024, 3, 7))
+kps = torch.from_numpy(synthetic.make_keypoints(B, seed=1)).cuda()
+kw = dict(kk=synthetic.KITTI_K, kind=L_.IN_KPS, kernel='tile')
+lib = L_.lib()
+buf = torch.zeros(256, dtype=torch.int64, device='cuda')
+for _ in range(3):
+    eng.forward(kps, **kw)
+torch.cuda.synchronize()
+L_.check(lib.mlb_debug_fwd_marks(C.c_void_p(buf.data_ptr())), 'marks')
+eng.forward(kps, **kw)
+torch.cuda.synchronize()
+L_.check(lib.mlb_debug_fwd_marks(C.c_void_p(0)), 'marks')
+m = buf.cpu().numpy().astype(np.int64)
+t0 = m[0]
+n_ops = eng.packed.desc['n_ops']
+print('input staged %.1f us' % ((m[1] - t0) / 1e3))
+prev = m[1]
+for i in range(n_ops):
+    g, e, s, w = m[2 + 4 * i:6 + 4 * i]
+    if g == 0:
+        continue
+    print('op %2d: gemm %.1f  epilogue %.1f  sync %.1f  act write %.1f   (us)' % (i, (g - prev) / 1e3, (e - g) / 1e3, (s - e) / 1e3, (w - s) / 1e3))
+    prev = w
+print('heads done +%.1f us, rows stored +%.1f us, total %.1f us' % ((m[2 + 4 * n_ops] - prev) / 1e3, (m[3 + 4 * n_ops] - m[2 + 4 * n_ops]) / 1e3, (m[3 + 4 * n_ops] - t0) / 1e3))
