@@ -269,21 +269,9 @@ __device__ __forceinline__ bool slot_valid(int slot, int rows_here, int& r) {
 }
 
 // narrow head forward: outs[slot][col0 + o] = bias[o] + sum_k act[k][slot] * W[o][k]   (one warp per output column)
-__device__ void head_forward(const float* __restrict__ W, const float* __restrict__ bias, int N, int K, const float* act,
-                             float* outs, int col0, int warp, int lane) {
-    for (int o = warp; o < N; o += NT / 32) {
-        const float* w = W + (size_t)o * K;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < K; k += 4) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
-            a0 = fmaf(act[(k + 0) * MP + lane], wv.x, a0);
-            a1 = fmaf(act[(k + 1) * MP + lane], wv.y, a1);
-            a2 = fmaf(act[(k + 2) * MP + lane], wv.z, a2);
-            a3 = fmaf(act[(k + 3) * MP + lane], wv.w, a3);
-        }
-        outs[lane * OUT_LD + col0 + o] = ((a0 + a1) + (a2 + a3)) + __ldg(bias + o);
-    }
+__device__ __forceinline__ void head_forward(const float* __restrict__ W, const float* __restrict__ bias, int N, int K,
+                                             const float* act, float* outs, int col0, int warp, int lane) {
+    for (int o = warp; o < N; o += NT / 32) outs[lane * OUT_LD + col0 + o] = head_column(W + (size_t)o * K, __ldg(bias + o), K, act, lane);
 }
 
 // aux head (after LocoModel.w2) and, in the final phase, the w_fin head + fused MultiTaskLoss and its gradient g_out
