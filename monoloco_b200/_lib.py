@@ -15,7 +15,7 @@ OP_GEMM, OP_HEAD = 0, 1
 F_RELU, F_SAVE_RES, F_ADD_RES, F_DROPOUT, F_IN_XIN = 1, 2, 4, 8, 16
 DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
 IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
-FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH = 1, 2, 4, 8, 16, 32
+FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH, FWD_FORCE_WIDE = 1, 2, 4, 8, 16, 32, 64
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',

@@ -166,11 +166,12 @@ __device__ __forceinline__ bool keep_draw(uint64_t seed, uint32_t site, uint32_t
     return drop_keep(drop_row_mix(drop_seed_mix(seed), row), drop_col_hash(col, site), drop_threshold(p));
 }
 
-// One output column of a narrow head for the 32 row slots of a tile:  bias + sum_k act[k][lane] * w[k]   (K % 128 == 0,
+// One output column of a narrow head, one row slot per lane:  bias + sum_k act[k * ld + slot] * w[k]   (K % 128 == 0,
 // K <= 1024, w 16-byte aligned).  The K weights are fetched ONCE, coalesced (up to 8 float4 per lane, a single L2 round
 // trip) and broadcast by shuffle; a uniform __ldg per 4 k paid one L2 latency every 32 k (measured 24 us per column at
 // K = 1024 in the tile forward kernel).  Accumulation order: 4 interleaved chains over increasing k.
-__device__ __forceinline__ float head_column(const float* __restrict__ w, float bias, int K, const float* act, int lane) {
+__device__ __forceinline__ float head_column(const float* __restrict__ w, float bias, int K, const float* act, int lane,
+                                             int slot, int ld) {
     float4 wr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -179,15 +180,15 @@ __device__ __forceinline__ float head_column(const float* __restrict__ w, float 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (i * 128 < K) {
-            const float* a = act + (size_t)(i * 128) * MP + lane;
+            const float* a = act + (size_t)(i * 128) * ld + slot;
 #pragma unroll 4
             for (int s = 0; s < 32; ++s) {
                 const float wx = __shfl_sync(0xffffffffu, wr[i].x, s), wy = __shfl_sync(0xffffffffu, wr[i].y, s);
                 const float wz = __shfl_sync(0xffffffffu, wr[i].z, s), ww = __shfl_sync(0xffffffffu, wr[i].w, s);
-                a0 = fmaf(a[(s * 4 + 0) * MP], wx, a0);
-                a1 = fmaf(a[(s * 4 + 1) * MP], wy, a1);
-                a2 = fmaf(a[(s * 4 + 2) * MP], wz, a2);
-                a3 = fmaf(a[(s * 4 + 3) * MP], ww, a3);
+                a0 = fmaf(a[(s * 4 + 0) * ld], wx, a0);
+                a1 = fmaf(a[(s * 4 + 1) * ld], wy, a1);
+                a2 = fmaf(a[(s * 4 + 2) * ld], wz, a2);
+                a3 = fmaf(a[(s * 4 + 3) * ld], ww, a3);
             }
         }
     }

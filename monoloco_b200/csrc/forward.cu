@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                     // ---- narrow head: one warp per output column, lane = tile row slot
                     for (int o = nwarps - 1 - warp; o < op.N; o += nwarps)
                         outs[lane * OUT_LD + op.out_col + o] = head_column(p.blob + op.w_off + (size_t)o * op.K,
-                                                                           __ldg(p.blob + op.shift_off + o), op.K, act, lane);
+                                                                           __ldg(p.blob + op.shift_off + o), op.K, act, lane, lane, MP);
                     fmark(marks, 5 + 4 * oi);
                 }
             }
@@ -627,6 +627,13 @@ size_t mlb_small_smem_bytes(int L);
 cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, long long* slab_off, cudaStream_t st);
 cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st);
 int mlb_small_max_clusters(int L);
+// forward_wide.cu
+size_t mlb_wide_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab_off);
+cudaError_t mlb_wide_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, const long long* slab_off, cudaStream_t st);
+bool mlb_wide_supported(int L, int n_sms);
+int mlb_wide_barriers(const mlb_op* ops, int n_ops);
+cudaError_t mlb_wide_launch(const FwdParams& p, const float* wslab, const long long* wslab_off, float* xg, unsigned* bar,
+                            unsigned bar_base, cudaStream_t st);
 
 struct mlb_model {
     mlb_model_desc desc;
@@ -638,6 +645,11 @@ struct mlb_model {
     float* slab_dev;               // slab-major W^T copies for the small-batch cluster kernel (L == 1024 only)
     long long slab_off[MLB_MAX_OPS];
     int small_conc;                // co-resident 8-CTA clusters (cudaOccupancyMaxActiveClusters)
+    float* wslab_dev;              // per-CTA column slabs for the whole-grid latency kernel (forward_wide.cu), or null
+    long long wslab_off[MLB_MAX_OPS];
+    float* wide_xg;                // [2][L][32] inter-CTA exchange tiles
+    unsigned* wide_bar;            // monotonic grid-barrier counter
+    unsigned wide_bar_count;       // host copy of the counter after the launches issued so far
     float* res_scratch;
     size_t res_floats;
     int* err_flag_dev;
@@ -740,6 +752,17 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
         m->small_conc = mlb_small_max_clusters(L);
         if (m->small_conc < 1) m->small_conc = 8;
     }
+    if (mlb_wide_supported(L, m->n_sms)) {
+        const size_t wf = mlb_wide_slab_floats(m->ops, desc->n_ops, L, m->wslab_off);
+        CU(cudaMalloc(&m->wslab_dev, wf * sizeof(float)));
+        CU(mlb_wide_pack(m->blob_dev, m->ops, desc->n_ops, L, m->wslab_dev, m->wslab_off, 0));
+        CU(cudaMalloc(&m->wide_xg, (size_t)2 * L * 32 * sizeof(float)));
+        CU(cudaMemset(m->wide_xg, 0, (size_t)2 * L * 32 * sizeof(float)));
+        CU(cudaMalloc(&m->wide_bar, sizeof(unsigned)));
+        CU(cudaMemset(m->wide_bar, 0, sizeof(unsigned)));
+        m->wide_bar_count = 0;
+        CU(cudaDeviceSynchronize());
+    }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
     CU(cudaMalloc(&m->err_flag_dev, sizeof(int)));
@@ -755,6 +778,8 @@ extern "C" int mlb_update_weights(mlb_handle h, const float* packed_host, size_t
     CU(cudaMemcpyAsync(h->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     if (h->slab_dev)
         CU(mlb_small_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->slab_dev, h->slab_off, (cudaStream_t)stream));
+    if (h->wslab_dev)
+        CU(mlb_wide_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->wslab_dev, h->wslab_off, (cudaStream_t)stream));
     return 0;
 }
 
@@ -763,6 +788,9 @@ extern "C" void mlb_destroy(mlb_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->blob_dev);
     cudaFree(h->slab_dev);
+    cudaFree(h->wslab_dev);
+    cudaFree(h->wide_xg);
+    cudaFree(h->wide_bar);
     cudaFree(h->res_scratch);
     cudaFree(h->err_flag_dev);
     cudaFree(h->st_in);
@@ -847,6 +875,22 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     for (int i = 0; i < a->n_gather; ++i) {
         if (!a->gather[i]) return fail("mlb_forward: null gather pointer");
         p.gather[i] = a->gather[i];
+    }
+
+    // ---- one image's worth of detections (<= 32 rows): the whole grid on one tile (forward_wide.cu)
+    const bool forced_other = (a->flags & (MLB_FWD_FORCE_TILE | MLB_FWD_FORCE_CLUSTER)) != 0 || a->rows_per_group != 0;
+    if (a->flags & MLB_FWD_FORCE_WIDE) {
+        if (h->wslab_dev == nullptr) return fail("mlb_forward: the whole-grid kernel is not available for this model / device");
+        if (a->n_rows > 32) return fail("mlb_forward: the whole-grid kernel takes at most 32 rows");
+    }
+    if (h->wslab_dev != nullptr && a->n_rows <= 32 && ((a->flags & MLB_FWD_FORCE_WIDE) || !forced_other)) {
+        p.n_tiles = 1;
+        const unsigned base = h->wide_bar_count;
+        h->wide_bar_count += (unsigned)mlb_wide_barriers(h->ops, d.n_ops) * (unsigned)(d.linear_size / 8);
+        cudaError_t ew = mlb_wide_launch(p, h->wslab_dev, h->wslab_off, h->wide_xg, h->wide_bar, base, st);
+        if (ew != cudaSuccess) return fail(std::string("loco_forward_wide_kernel launch: ") + cudaGetErrorString(ew));
+        g_launches++;
+        return 0;
     }
 
     // ---- small batches: 8-CTA cluster per 16 detections (forward_small.cu) when that finishes sooner than row tiles.

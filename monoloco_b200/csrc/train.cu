@@ -271,7 +271,7 @@ __device__ __forceinline__ bool slot_valid(int slot, int rows_here, int& r) {
 // narrow head forward: outs[slot][col0 + o] = bias[o] + sum_k act[k][slot] * W[o][k]   (one warp per output column)
 __device__ __forceinline__ void head_forward(const float* __restrict__ W, const float* __restrict__ bias, int N, int K,
                                              const float* act, float* outs, int col0, int warp, int lane) {
-    for (int o = warp; o < N; o += NT / 32) outs[lane * OUT_LD + col0 + o] = head_column(W + (size_t)o * K, __ldg(bias + o), K, act, lane);
+    for (int o = warp; o < N; o += NT / 32) outs[lane * OUT_LD + col0 + o] = head_column(W + (size_t)o * K, __ldg(bias + o), K, act, lane, lane, MP);
 }
 
 // aux head (after LocoModel.w2) and, in the final phase, the w_fin head + fused MultiTaskLoss and its gradient g_out

@@ -272,3 +272,72 @@ def test_cluster_kernel_stereo_dropout_and_legacy_models():
     ok, worst = O.close(out['raw'].cpu().numpy(), g['out'])
     assert ok, worst
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ whole-grid latency kernel
+@pytest.mark.parametrize('B', [1, 2, 7, 16, 17, 31, 32])
+def test_wide_kernel_batches_vs_oracle(mono1024, B):
+    """Whole-grid kernel (forward_wide.cu): every layer split by output columns over L/8 CTAs, grid barrier + TMA
+    exchange per layer; both row-slot instantiations (<= 16, <= 32), repeated launches (monotonic barrier counter)."""
+    O, synthetic, engine, L_ = _mods()
+    sd, eng = mono1024
+    kps = synthetic.make_keypoints(B, seed=140 + B)
+    x = O.preprocess_monoloco(kps, synthetic.KITTI_K)
+    ref = O.loco_model_forward(sd, x)
+    for rep in range(3):
+        out = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_x=True, want_xyzc=True,
+                          kernel='wide')
+        assert np.abs(out['x'].cpu().numpy() - x).max() < 6e-6
+        ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+        assert ok, (rep, worst)
+        _check_dec(O, out['dec'].cpu().numpy(), O.extract_outputs(ref), False)
+    tile = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_xyzc=True, kernel='tile')
+    assert torch.allclose(out['raw'], tile['raw'], rtol=2e-5, atol=2e-5) and torch.allclose(out['xyzc'], tile['xyzc'], rtol=1e-5, atol=1e-5)
+    auto = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS)   # <= 32 rows: selected by default
+    assert torch.equal(auto['raw'], out['raw'])
+    with pytest.raises(RuntimeError):
+        eng.forward(torch.from_numpy(synthetic.make_keypoints(33, seed=1)).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, kernel='wide')
+
+
+def test_wide_kernel_stereo_dropout_and_legacy_models():
+    O, synthetic, engine, L_ = _mods()
+    f = np.load(os.path.join(GOLDEN, 'ref_loco_stereo.npz'))
+    sd = synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2)
+    eng = engine.LocoEngine(sd)
+    left, right = torch.from_numpy(f['left'][:3]).cuda(), torch.from_numpy(f['right']).cuda()   # 3 x 9 = 27 pairs
+    out = eng.forward(left, x_right=right, kk=f['K'], kind=L_.IN_KPS_STEREO, want_x=True, kernel='wide')
+    n = out['raw'].shape[0]
+    assert n == 3 * f['right'].shape[0] <= 32
+    assert np.abs(out['x'].cpu().numpy() - f['pairs_x'][:n]).max() < 6e-6
+    ok, worst = O.close(out['raw'].cpu().numpy(), f['pairs_raw'][:n])
+    assert ok, worst
+    eng.close()
+    # MC-dropout: explicit masks vs the oracle, in-kernel RNG vs the tile kernel
+    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+    eng = engine.LocoEngine(sd)
+    B = 23
+    masks = (np.random.RandomState(3).uniform(size=(2, B, 1024)) >= 0.2).astype(np.uint8)
+    x = synthetic.make_inputs(B, 34, seed=31)
+    ref = O.loco_model_forward(sd, x, drop_masks=(masks[0], masks[1]), p_dropout=0.2)
+    out = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_mask=torch.from_numpy(masks).cuda(), kernel='wide')
+    ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+    assert ok, worst
+    a = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='wide')['raw']
+    b = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='tile')['raw']
+    assert torch.allclose(a, b, rtol=2e-5, atol=2e-5)
+    eng.close()
+    # legacy MonolocoModel widths: L = 1024 (128 CTAs) and L = 256 (32 CTAs)
+    for name, args in (('ref_fwd_monoloco_l1024_o9.npz', ('monoloco', 34, 9, 1024, 3, 3)),):
+        g = np.load(os.path.join(GOLDEN, name))
+        eng = engine.LocoEngine(synthetic.make_state_dict(*args))
+        out = eng.forward(torch.from_numpy(g['x'][:32]).cuda(), kernel='wide')
+        ok, worst = O.close(out['raw'].cpu().numpy(), g['out'][:32])
+        assert ok, worst
+        eng.close()
+    sd = synthetic.make_state_dict('monoloco', 34, 2, 256, 3, 5)
+    eng = engine.LocoEngine(sd)
+    x = synthetic.make_inputs(9, 34, seed=2)
+    out = eng.forward(torch.from_numpy(x).cuda(), kernel='wide')
+    ok, worst = O.close(out['raw'].cpu().numpy(), O.monoloco_model_forward(sd, x))
+    assert ok, worst
+    eng.close()
