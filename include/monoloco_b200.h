@@ -89,7 +89,7 @@ enum { MLB_FWD_ZERO_CENTER = 1, /* preprocess_monoloco(zero_center=True) (net.py
        MLB_FWD_FORCE_TILE    = 8,  /* always use the throughput kernel (one CTA per row tile)        */
        MLB_FWD_FORCE_CLUSTER = 16, /* always use the small-batch kernel (8-CTA cluster per 16 rows)  */
        MLB_FWD_RES_SCRATCH   = 32, /* stash the residual in the L2-resident global scratch instead   */
-       MLB_FWD_FORCE_WIDE    = 64  /* always use the whole-grid latency kernel (<= 32 rows)          */ };
+       MLB_FWD_FORCE_WIDE    = 64  /* always use the whole-grid latency kernel (one launch / 32 rows)*/ };
 
 typedef struct mlb_forward_args {
     int32_t input_kind;     /* MLB_IN_*                                                             */

@@ -195,4 +195,43 @@ __device__ __forceinline__ float head_column(const float* __restrict__ w, float 
     return ((a0 + a1) + (a2 + a3)) + bias;
 }
 
+// All N <= 16 output columns of a narrow head, K split over the warps of the CTA (warp w: k in [128w, 128w + 128), K == 128 *
+// nwarps), one row slot per lane.  Lane l fetches W[o][128w + 4l .. +3] for every column (N coalesced float4 loads, one
+// L2 round trip) and the warp broadcasts them by shuffle.  Partial sums go to part[(w * 16 + o) * 32 + lane]; after the
+// caller's barrier, head_ksplit_sum() adds the nwarps partials in a fixed order.
+__device__ __forceinline__ void head_ksplit_partial(const float* __restrict__ W, int N, int K, const float* act, int warp, int lane,
+                                                    int slot, int ld, float* part) {
+    float4 wr[16];
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        acc[o] = 0.f;
+        wr[o] = o < N ? __ldg(reinterpret_cast<const float4*>(W + (size_t)o * K + warp * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* a = act + (size_t)(warp * 128) * ld + slot;
+#pragma unroll 2
+    for (int s = 0; s < 32; ++s) {
+        const float a0 = a[(s * 4 + 0) * ld], a1 = a[(s * 4 + 1) * ld], a2 = a[(s * 4 + 2) * ld], a3 = a[(s * 4 + 3) * ld];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+            if (o < N) {
+                float t = acc[o];
+                t = fmaf(a0, __shfl_sync(0xffffffffu, wr[o].x, s), t);
+                t = fmaf(a1, __shfl_sync(0xffffffffu, wr[o].y, s), t);
+                t = fmaf(a2, __shfl_sync(0xffffffffu, wr[o].z, s), t);
+                t = fmaf(a3, __shfl_sync(0xffffffffu, wr[o].w, s), t);
+                acc[o] = t;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 16; ++o)
+        if (o < N) part[(warp * 16 + o) * 32 + lane] = acc[o];
+}
+__device__ __forceinline__ float head_ksplit_sum(const float* part, int nwarps, int o, int lane, float bias) {
+    float v = 0.f;
+    for (int w = 0; w < nwarps; ++w) v += part[(w * 16 + o) * 32 + lane];
+    return v + bias;
+}
+
 }  // namespace mlb

@@ -7,11 +7,12 @@
 //
 //   CTA c owns columns [8c, 8c+8) of every layer.  Its weights are one contiguous slab  Wt[k][8]  per layer (32 KB at
 //   K = 1024, re-packed at mlb_create), streamed by TMA through a 2-stage ring that runs ahead of the layer loop.
-//   Per layer:  256 threads = (k-subset, row) compute partial sums of the [R x 8] block  ->  shared-memory reduction ->
+//   Per layer:  256 threads = (k-subset, row pair) compute partial sums of the [R x 8] block  ->  shared-memory reduction ->
 //   folded-BN / ReLU / dropout / residual epilogue (one output per thread, residual kept in that thread's register) ->
 //   the block goes to a global k-major exchange buffer xg[parity][L][R] -> grid barrier -> every CTA pulls the complete
 //   next-layer input tile (L x R floats, L2-resident) back into shared memory with one TMA bulk copy.
-//   Narrow heads, decode and the stores run on CTA 0 (the other CTAs exit after the last exchange).
+//   Narrow heads (the same slab code over zero-padded [K][8] head slabs), decode and the stores run on CTA 0; the
+//   other CTAs exit after the last exchange.
 //
 // Cooperative launch (co-residency for the hand-rolled grid barrier); the barrier counter is monotonic across launches
 // (the host passes the base value), so no memset precedes the kernel.
@@ -27,9 +28,10 @@ namespace mlb {
 constexpr int WC = 8;        // output columns per CTA
 constexpr int WNT = 256;     // threads per CTA
 constexpr int WNST = 2;      // weight-slab ring stages
+constexpr int WPART = 8 * 16 * 32;  // floats of the partial-sum buffer
 
 struct WideExtra {
-    const float* wslab;                // per GEMM op: [L/8 CTAs][Kpad][8]
+    const float* wslab;                // per GEMM op: [L/8 CTAs][Kpad][8]; per head op: [ceil(N/8)][K][8]
     long long wslab_off[MLB_MAX_OPS];  // float offset of each op's slab block
     float* xg;                         // [2][L][32] exchange buffer (k-major tiles, double-buffered by layer parity)
     unsigned* bar;                     // monotonic grid-barrier counter
@@ -42,22 +44,34 @@ __device__ __forceinline__ unsigned wide_ld_acquire(const unsigned* ptr) {
     return v;
 }
 
+// profiling aid (mlb_debug_fwd_marks): thread 0 of CTA 0 (and of CTA 64, at +128) stamps globaltimer along the layer loop
+__device__ unsigned long long* g_wide_marks = nullptr;
+__device__ __forceinline__ void wmark(unsigned long long* marks, int slot) {
+    if (marks != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        marks[slot] = t;
+    }
+}
+
 template <int R>  // row slots of the tile: 16 or 32
 __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_constant__ FwdParams p,
                                                                    const __grid_constant__ WideExtra ex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int S = WNT / R;  // k-subsets: thread (s, r) accumulates k = s, s + S, s + 2S, ...
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int S = 2 * WNT / R;  // k-subsets: thread (s, row pair q) accumulates k = s, s + S, s + 2S, ... for rows 2q, 2q+1
+    const int tid = threadIdx.x;
     const int cta = blockIdx.x, L = p.L;
 
     float* act = reinterpret_cast<float*>(smem_raw);   // [L][R]  k-major input tile of the current layer
     float* ring = act + (size_t)L * R;                  // [WNST][L][WC] weight slabs
     float* part = ring + (size_t)WNST * L * WC;         // [S][WC][R] partial sums
-    float* outs = part + WNT * WC;                      // [R][OUT_LD]
+    float* outs = part + WPART;                         // [R][OUT_LD]
     float* cen = outs + R * OUT_LD;                     // [R][4]
     uint64_t* wfull = reinterpret_cast<uint64_t*>(cen + R * 4);  // [WNST]
     uint64_t* gfull = wfull + WNST;                     // exchange-tile arrival
 
+    unsigned long long* marks = (tid == 0 && (cta == 0 || cta == 64) && g_wide_marks != nullptr) ? g_wide_marks + (cta ? 128 : 0) : nullptr;
+    wmark(marks, 0);
     if (tid == 0) {
         for (int s = 0; s < WNST; ++s) mbar_init(&wfull[s], 1);
         mbar_init(gfull, 1);
@@ -66,75 +80,99 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
     for (int i = tid; i < R * OUT_LD; i += WNT) outs[i] = 0.f;
     __syncthreads();
 
-    // ---- weight stream: GEMM op #g -> ring stage g % WNST (issued by thread 0, two layers ahead)
-    int gemm_ops[MLB_MAX_OPS];
-    int n_gemm = 0;
-    for (int oi = 0; oi < p.n_ops; ++oi)
-        if (p.ops[oi].type == MLB_OP_GEMM) gemm_ops[n_gemm++] = oi;
-    auto issue_slab = [&](int g) {
-        const mlb_op& op = p.ops[gemm_ops[g]];
-        const uint32_t bytes = (uint32_t)(op.Kpad * WC * sizeof(float));
-        const int st = g % WNST;
+    // ---- weight stream.  Item = one [Kpad][8] slab: every GEMM op contributes the CTA's column slab; on CTA 0 (which
+    // also runs the narrow heads) a head op contributes ceil(N / 8) zero-padded slabs.  Item i lives in ring stage
+    // i % WNST and is issued by thread 0 two items ahead of its use.
+    auto n_items_of = [&](const mlb_op& op) { return op.type == MLB_OP_GEMM ? 1 : (cta == 0 ? (op.N + WC - 1) / WC : 0); };
+    int n_items = 0;
+    for (int oi = 0; oi < p.n_ops; ++oi) n_items += n_items_of(p.ops[oi]);
+    int issue_op = 0, issue_sub = 0, issued = 0;  // stream cursor (thread 0)
+    auto issue_next = [&]() {
+        while (issue_op < p.n_ops && issue_sub >= n_items_of(p.ops[issue_op])) issue_op++, issue_sub = 0;
+        if (issue_op >= p.n_ops) return;
+        const mlb_op& op = p.ops[issue_op];
+        const bool gemm = op.type == MLB_OP_GEMM;
+        const int kp = gemm ? op.Kpad : op.K;
+        const uint32_t bytes = (uint32_t)(kp * WC * sizeof(float));
+        const float* src = ex.wslab + ex.wslab_off[issue_op] + (size_t)(gemm ? cta : issue_sub) * kp * WC;
+        const int st = issued % WNST;
         mbar_expect_tx(&wfull[st], bytes);
-        tma_bulk_g2s(ring + (size_t)st * L * WC, ex.wslab + ex.wslab_off[gemm_ops[g]] + (size_t)cta * op.Kpad * WC, bytes, &wfull[st]);
+        tma_bulk_g2s(ring + (size_t)st * L * WC, src, bytes, &wfull[st]);
+        issued++, issue_sub++;
     };
     if (tid == 0)
-        for (int g = 0; g < WNST && g < n_gemm; ++g) issue_slab(g);
+        for (int i = 0; i < WNST; ++i) issue_next();
 
-    const int rows_here = p.n_rows;  // <= R, a single tile
-    stage_input_tile(p, 0, rows_here, R, R, act, cen, tid, WNT, [] { __syncthreads(); });
+    const int row0 = p.row_base;
+    const int rows_here = min(R, p.n_rows - row0);  // a single tile
+    stage_input_tile(p, row0, rows_here, R, R, act, cen, tid, WNT, [] { __syncthreads(); });
     __syncthreads();
     if (cta == 0 && p.out_x != nullptr && p.input_kind != MLB_IN_X) {
         for (int idx = tid; idx < rows_here * p.in_size; idx += WNT) {
             const int r = idx / p.in_size, k = idx % p.in_size;
-            p.out_x[(size_t)r * p.in_size + k] = act[k * R + r];
+            p.out_x[(size_t)(row0 + r) * p.in_size + k] = act[k * R + r];
         }
     }
+    wmark(marks, 1);
 
-    // GEMM mapping: k-subset s, row r.  R = 32: s = warp, r = lane;  R = 16: s = 2 * warp + (lane >> 4), r = lane & 15
-    const int gs = tid / R, gr = tid % R;
-    // epilogue mapping (threads < WC * R): column ec of the CTA's 8, row er
+    // GEMM mapping: k-subset gs, row pair gq (a warp covers 32 / (R/2) consecutive k: contiguous, conflict-free LDS.64)
+    const int gs = tid / (R / 2), gq = tid % (R / 2);
+    // reduce / epilogue mapping (threads < WC * R): column ec of the slab's 8, row er
     const int ec = tid / R, er = tid % R;
     const bool epi = tid < WC * R;
     const int gcol = cta * WC + ec;
+    int item = 0;  // items consumed so far
+    // partial sums of the [R x 8] block of the slab in ring stage item % WNST over K = kp, reduced into `v` of thread (ec, er)
+    auto slab_block = [&](int kp) -> float {
+        const int st = item % WNST;
+        mbar_wait(&wfull[st], (item / WNST) & 1, p.err_flag);
+        const float* w = ring + (size_t)st * L * WC;
+        // two rows per thread: one LDS.64 of activations + two broadcast LDS.128 of weights feed 16 FMAs
+        float acc0[WC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, acc1[WC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int k = gs; k < kp; k += S) {
+            const float2 a = *reinterpret_cast<const float2*>(act + k * R + 2 * gq);
+            const float4 w0 = *reinterpret_cast<const float4*>(w + k * WC);
+            const float4 w1 = *reinterpret_cast<const float4*>(w + k * WC + 4);
+            const float wv[WC] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int c = 0; c < WC; ++c) acc0[c] = fmaf(a.x, wv[c], acc0[c]), acc1[c] = fmaf(a.y, wv[c], acc1[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < WC; ++c) *reinterpret_cast<float2*>(part + (gs * WC + c) * R + 2 * gq) = make_float2(acc0[c], acc1[c]);
+        __syncthreads();  // partials complete; nobody reads this ring stage any more
+        item++;
+        if (tid == 0) issue_next();
+        float v = 0.f;
+        if (epi) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) v += part[(s * WC + ec) * R + er];
+        }
+        return v;
+    };
+
     float res = 0.f;
     int site = 0, g = 0, par = 0;
     unsigned bar_target = ex.bar_base;
+    int n_gemm = 0;
+    for (int oi = 0; oi < p.n_ops; ++oi) n_gemm += p.ops[oi].type == MLB_OP_GEMM;
 
     for (int oi = 0; oi < p.n_ops; ++oi) {
         const mlb_op& op = p.ops[oi];
         if (op.type == MLB_OP_GEMM) {
-            const int st = g % WNST;
-            mbar_wait(&wfull[st], (g / WNST) & 1, p.err_flag);
-            const float* w = ring + (size_t)st * L * WC;
-            float acc[WC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-            for (int k = gs; k < op.Kpad; k += S) {
-                const float a = act[k * R + gr];
-                const float4 w0 = *reinterpret_cast<const float4*>(w + k * WC);
-                const float4 w1 = *reinterpret_cast<const float4*>(w + k * WC + 4);
-                acc[0] = fmaf(a, w0.x, acc[0]), acc[1] = fmaf(a, w0.y, acc[1]);
-                acc[2] = fmaf(a, w0.z, acc[2]), acc[3] = fmaf(a, w0.w, acc[3]);
-                acc[4] = fmaf(a, w1.x, acc[4]), acc[5] = fmaf(a, w1.y, acc[5]);
-                acc[6] = fmaf(a, w1.z, acc[6]), acc[7] = fmaf(a, w1.w, acc[7]);
-            }
-#pragma unroll
-            for (int c = 0; c < WC; ++c) part[(gs * WC + c) * R + gr] = acc[c];
-            __syncthreads();  // partials complete; nobody reads `act` / this ring stage any more
-            if (tid == 0 && g + WNST < n_gemm) issue_slab(g + WNST);
+            wmark(marks, 2 + 4 * g);
+            float v = slab_block(op.Kpad);
+            wmark(marks, 3 + 4 * g);
             const bool last_gemm = g + 1 == n_gemm;
             if (epi) {
-                float v = 0.f;
-#pragma unroll
-                for (int s = 0; s < S; ++s) v += part[(s * WC + ec) * R + er];
                 v = fmaf(v, __ldg(p.blob + op.scale_off + gcol), __ldg(p.blob + op.shift_off + gcol));
                 if (op.flags & MLB_F_RELU) v = fmaxf(v, 0.f);
                 if ((op.flags & MLB_F_DROPOUT) && (p.flags & MLB_FWD_DROPOUT)) {
                     bool keep;
                     if (p.drop_mask != nullptr)
-                        keep = er < p.n_rows ? p.drop_mask[((size_t)site * p.n_rows + er) * L + gcol] != 0 : true;
+                        keep = er < rows_here ? p.drop_mask[((size_t)site * p.n_rows + row0 + er) * L + gcol] != 0 : true;
                     else
-                        keep = keep_draw(p.drop_seed, site, er, gcol, p.p_drop);
+                        keep = keep_draw(p.drop_seed, site, row0 + er, gcol, p.p_drop);
                     v = keep ? v * (1.0f / (1.0f - p.p_drop)) : 0.f;
                 }
                 if (op.flags & MLB_F_ADD_RES) v += res;
@@ -159,6 +197,7 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
                         __trap();
                     }
                 }
+                wmark(marks, 4 + 4 * g);
                 asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy stores -> this async-proxy read
                 const uint32_t bytes = (uint32_t)((size_t)L * R * sizeof(float));
                 mbar_expect_tx(gfull, bytes);
@@ -168,20 +207,25 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
                                  min(32768u, bytes - off), gfull);
             }
             mbar_wait(gfull, g & 1, p.err_flag);
+            wmark(marks, 5 + 4 * g);
             par ^= 1;
             g++;
         } else if (cta == 0) {
-            // ---- narrow head on CTA 0: one warp per output column, lane = row slot
-            for (int o = 7 - warp; o < op.N; o += 8) {
-                const float y = head_column(p.blob + op.w_off + (size_t)o * op.K, __ldg(p.blob + op.shift_off + o), op.K, act, lane,
-                                            lane & (R - 1), R);
-                if (lane < R) outs[lane * OUT_LD + op.out_col + o] = y;
+            // ---- narrow head on CTA 0: the same slab code over ceil(N / 8) zero-padded [K][8] slabs
+            for (int sub = 0; sub * WC < op.N; ++sub) {
+                const float v = slab_block(op.K);
+                const int o = sub * WC + ec;
+                if (epi && o < op.N) outs[er * OUT_LD + op.out_col + o] = v + __ldg(p.blob + op.shift_off + o);
+                __syncthreads();  // `part` is rewritten by the next slab
             }
+            wmark(marks, 2 + 4 * g);
         }
     }
     // ---- decode + store (CTA 0, one thread per row)
     __syncthreads();
-    if (tid < rows_here) store_row(p, (size_t)tid, outs + tid * OUT_LD, cen + tid * 4);
+    wmark(marks, 2 + 4 * n_gemm);
+    if (tid < rows_here) store_row(p, (size_t)row0 + tid, outs + tid * OUT_LD, cen + tid * 4);
+    wmark(marks, 3 + 4 * n_gemm);
 }
 
 // W^T [Kpad][L] -> per-CTA slabs [L/8][Kpad][8]
@@ -195,7 +239,7 @@ __global__ void wide_pack_kernel(const float* __restrict__ wt, float* __restrict
 
 template <int R>
 static size_t wide_smem(int L) {
-    return ((size_t)L * R + (size_t)WNST * L * WC + (size_t)WNT * WC + (size_t)R * OUT_LD + (size_t)R * 4) * sizeof(float) +
+    return ((size_t)L * R + (size_t)WNST * L * WC + (size_t)WPART + (size_t)R * OUT_LD + (size_t)R * 4) * sizeof(float) +
            (WNST + 1) * sizeof(uint64_t);
 }
 
@@ -203,14 +247,28 @@ static size_t wide_smem(int L) {
 
 using namespace mlb;
 
-// total floats of the per-CTA slab copy and each op's offset in it
+cudaError_t mlb_wide_set_marks(unsigned long long* ptr) { return cudaMemcpyToSymbol(mlb::g_wide_marks, &ptr, sizeof(ptr)); }
+
+// head weights W[N][K] -> ceil(N/8) zero-padded k-major slabs [K][8]
+__global__ void wide_pack_head_kernel(const float* __restrict__ w, float* __restrict__ slab, int N, int K) {
+    const int nsub = (N + mlb::WC - 1) / mlb::WC;
+    const int n = nsub * K * mlb::WC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int sub = i / (K * mlb::WC), k = (i / mlb::WC) % K, c = i % mlb::WC;
+        const int o = sub * mlb::WC + c;
+        slab[i] = o < N ? w[(size_t)o * K + k] : 0.f;
+    }
+}
+
+// total floats of the slab copy and each op's offset in it (GEMM: [L/8][Kpad][8]; head: [ceil(N/8)][K][8])
 size_t mlb_wide_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab_off) {
     size_t off = 0;
     for (int i = 0; i < n_ops; ++i) {
-        slab_off[i] = -1;
-        if (ops[i].type != MLB_OP_GEMM) continue;
         slab_off[i] = (long long)off;
-        off += (size_t)ops[i].Kpad * L;
+        if (ops[i].type == MLB_OP_GEMM)
+            off += (size_t)ops[i].Kpad * L;
+        else
+            off += (size_t)((ops[i].N + WC - 1) / WC) * ops[i].K * WC;
     }
     return off;
 }
@@ -218,8 +276,10 @@ size_t mlb_wide_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab
 cudaError_t mlb_wide_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, const long long* slab_off,
                           cudaStream_t st) {
     for (int i = 0; i < n_ops; ++i) {
-        if (ops[i].type != MLB_OP_GEMM) continue;
-        wide_pack_kernel<<<128, 256, 0, st>>>(blob + ops[i].w_off, slab + slab_off[i], ops[i].Kpad, L);
+        if (ops[i].type == MLB_OP_GEMM)
+            wide_pack_kernel<<<128, 256, 0, st>>>(blob + ops[i].w_off, slab + slab_off[i], ops[i].Kpad, L);
+        else
+            wide_pack_head_kernel<<<32, 256, 0, st>>>(blob + ops[i].w_off, slab + slab_off[i], ops[i].N, ops[i].K);
     }
     return cudaGetLastError();
 }
@@ -252,7 +312,7 @@ cudaError_t mlb_wide_launch(const FwdParams& p, const float* wslab, const long l
     ex.xg = xg, ex.bar = bar, ex.bar_base = bar_base;
     void* args[] = {(void*)&p, (void*)&ex};
     const int grid = p.L / WC;
-    if (p.n_rows <= 16)
+    if (p.n_rows - p.row_base <= 16)
         return cudaLaunchCooperativeKernel((void*)loco_forward_wide_kernel<16>, dim3(grid), dim3(WNT), args, wide_smem<16>(p.L), st);
     return cudaLaunchCooperativeKernel((void*)loco_forward_wide_kernel<32>, dim3(grid), dim3(WNT), args, wide_smem<32>(p.L), st);
 }

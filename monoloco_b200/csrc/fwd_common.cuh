@@ -11,6 +11,7 @@ struct FwdParams {
     mlb_op ops[MLB_MAX_OPS];
     int n_ops, in_size, out_size, L, decode_kind;
     int input_kind, flags, n_rows, n_right, n_tiles, kpad0;
+    int row_base;  // forward_wide.cu: first row of the single tile this launch processes
     float kinv[9];
     float z_met;
     const float* x;

@@ -7,9 +7,10 @@ from monoloco_b200 import synthetic, _lib as L_
 from monoloco_b200.engine import LocoEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+KERNEL = sys.argv[2] if len(sys.argv) > 2 else 'tile'
 eng = LocoEngine(synthetic.make_state_dict('loco', 34, 9, 1024, 3, 7))
 kps = torch.from_numpy(synthetic.make_keypoints(B, seed=1)).cuda()
-kw = dict(kk=synthetic.KITTI_K, kind=L_.IN_KPS, kernel='tile')
+kw = dict(kk=synthetic.KITTI_K, kind=L_.IN_KPS, kernel=KERNEL)
 lib = L_.lib()
 buf = torch.zeros(256, dtype=torch.int64, device='cuda')
 for _ in range(3):
@@ -23,6 +24,22 @@ m = buf.cpu().numpy().astype(np.int64)
 t0 = m[0]
 n_ops = eng.packed.desc['n_ops']
 print('input staged %.1f us' % ((m[1] - t0) / 1e3))
+if KERNEL == 'wide':
+  for base in (0, 128):
+    m = buf.cpu().numpy().astype(np.int64)[base:]
+    if m[0] == 0:
+        continue
+    print('CTA %d (start %+.1f us vs CTA 0)' % (64 if base else 0, (m[0] - t0) / 1e3))
+    prev = m[1]
+    for i in range(9):
+        a, b, c, d = m[2 + 4 * i:6 + 4 * i]
+        if c == 0:
+            c = d = b
+        print('gemm %d: wait weights %.1f  partial sums %.1f  epilogue+barrier %.1f  exchange %.1f  (us)' % (i, (a - prev) / 1e3, (b - a) / 1e3, (c - b) / 1e3, (d - c) / 1e3))
+        prev = d
+    if m[39]:
+        print('heads +%.1f us, stored +%.1f us, total %.1f us' % ((m[38] - prev) / 1e3, (m[39] - m[38]) / 1e3, (m[39] - t0) / 1e3))
+  sys.exit(0)
 prev = m[1]
 for i in range(n_ops):
     g, e, s, w = m[2 + 4 * i:6 + 4 * i]
