@@ -59,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 24)) {
-            if (err_flag) atomicExch(err_flag, ERR_MBAR_TIMEOUT);
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = ERR_MBAR_TIMEOUT;  // plain store: the flag may live in mapped host memory
             __threadfence_system();
             __trap();
         }
@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(128);
         if (++spins > (1u << 22)) {
-            if (err_flag) atomicExch(err_flag, ERR_MBAR_TIMEOUT);
+            if (err_flag) *reinterpret_cast<volatile int*>(err_flag) = ERR_MBAR_TIMEOUT;  // plain store: the flag may live in mapped host memory
             __threadfence_system();
             __trap();
         }

@@ -653,7 +653,8 @@ struct mlb_model {
     unsigned wide_bar_count;       // host copy of the counter after the launches issued so far
     float* res_scratch;
     size_t res_floats;
-    int* err_flag_dev;
+    int* err_flag_dev;             // device view of err_flag_host
+    int* err_flag_host;            // mapped pinned host word: the host reads it after a sync without a copy
     // staging for mlb_forward_host
     float* st_in;
     float* st_in_r;
@@ -767,8 +768,9 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
-    CU(cudaMalloc(&m->err_flag_dev, sizeof(int)));
-    CU(cudaMemset(m->err_flag_dev, 0, sizeof(int)));
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&m->err_flag_host), sizeof(int), cudaHostAllocMapped));
+    *m->err_flag_host = 0;
+    CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->err_flag_dev), m->err_flag_host, 0));
     *out = m;
     return 0;
 }
@@ -794,7 +796,7 @@ extern "C" void mlb_destroy(mlb_handle h) {
     cudaFree(h->wide_xg);
     cudaFree(h->wide_bar);
     cudaFree(h->res_scratch);
-    cudaFree(h->err_flag_dev);
+    cudaFreeHost(h->err_flag_host);
     cudaFree(h->st_in);
     cudaFree(h->st_in_r);
     cudaFree(h->st_raw);
@@ -992,14 +994,39 @@ extern "C" int mlb_forward_host(mlb_handle h, const mlb_forward_args* a, void* s
     dev.drop_mask = nullptr;
     dev.n_gather = 0;
     if (a->drop_mask) return fail("mlb_forward_host: drop_mask is a device-only option");
+    // One image's worth of rows: the kernel stores straight into the caller's buffers when they are pinned (mapped under
+    // UVA) -- a few posted PCIe writes from one CTA instead of three D2H copies.  Larger batches keep the DMA copies
+    // (row-at-a-time stores would turn into ~12 small PCIe writes per detection).
+    bool zero_copy = B <= 64;
+    void* dptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (zero_copy) {
+        void* hp[4] = {a->out_raw, a->out_dec, a->out_xyzc, a->out_x};
+        for (int i = 0; i < 4 && zero_copy; ++i) {
+            if (!hp[i]) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, hp[i]) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+                cudaGetLastError();
+                zero_copy = false;
+            } else {
+                dptr[i] = at.devicePointer;
+            }
+        }
+    }
+    if (zero_copy) {
+        dev.out_raw = static_cast<float*>(dptr[0]);
+        dev.out_dec = static_cast<float*>(dptr[1]);
+        dev.out_xyzc = static_cast<float*>(dptr[2]);
+        dev.out_x = static_cast<float*>(dptr[3]);
+    }
     if (mlb_forward(h, &dev, stream)) return -1;
-    CU(cudaMemcpyAsync(a->out_raw, h->st_raw, B * d.output_size * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (a->out_dec) CU(cudaMemcpyAsync(a->out_dec, h->st_dec, B * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (a->out_xyzc) CU(cudaMemcpyAsync(a->out_xyzc, h->st_xyzc, B * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (a->out_x) CU(cudaMemcpyAsync(a->out_x, h->st_x, B * d.input_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!zero_copy) {
+        CU(cudaMemcpyAsync(a->out_raw, h->st_raw, B * d.output_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (a->out_dec) CU(cudaMemcpyAsync(a->out_dec, h->st_dec, B * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (a->out_xyzc) CU(cudaMemcpyAsync(a->out_xyzc, h->st_xyzc, B * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (a->out_x) CU(cudaMemcpyAsync(a->out_x, h->st_x, B * d.input_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaStreamSynchronize(st));
-    int err = 0;
-    CU(cudaMemcpy(&err, h->err_flag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+    const int err = *reinterpret_cast<volatile int*>(h->err_flag_host);
     if (err) return fail("mlb_forward_host: device error flag " + std::to_string(err));
     return 0;
 }

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
                 unsigned spins = 0;
                 while ((int)(wide_ld_acquire(ex.bar) - bar_target) < 0) {
                     if (++spins > (1u << 24)) {
-                        if (p.err_flag != nullptr) atomicExch(p.err_flag, 3);
+                        if (p.err_flag != nullptr) *reinterpret_cast<volatile int*>(p.err_flag) = 3;
                         __threadfence_system();
                         __trap();
                     }
