@@ -169,6 +169,13 @@ def extras(eng, sd, dev):
             x = torch.from_numpy(synthetic.make_keypoints(b, seed=2)).to(dev)
             lat[str(b)] = timed(lambda: eng.forward(x, kk=synthetic.KITTI_K, kind=L_.IN_KPS), 20 if b <= 4096 else 3)
         out["forward_ms_by_batch"] = lat
+        # one image's worth of detections is the weight-streaming regime (B <= ~19): the whole-grid kernel's
+        # share of the HBM copy peak on the 33.8 MB it has to touch (L2-warm here, so this is an L2/HBM mix)
+        hbm_peak = peaks()[0]
+        wbytes = eng.packed.blob.size * 4
+        out["small_batch_roofline"] = {"rows": 16, "kernel": "loco_forward_wide_kernel", "ms": lat["16"],
+                                       "weight_bytes": wbytes, "achieved_GBps": wbytes / (lat["16"] * 1e-3) / 1e9,
+                                       "frac_of_hbm_copy_peak": wbytes / (lat["16"] * 1e-3) / 1e9 / hbm_peak}
         from monoloco_b200 import engine as E
         seng = E.LocoEngine(synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2), device=dev)
         le, ri = synthetic.make_keypoints(64, seed=3, right=True)
