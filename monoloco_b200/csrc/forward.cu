@@ -651,6 +651,7 @@ struct mlb_model {
     float* wide_xg;                // [2][L][32] inter-CTA exchange tiles
     unsigned* wide_bar;            // monotonic grid-barrier counter
     unsigned wide_bar_count;       // host copy of the counter after the launches issued so far
+    bool wide_disabled;            // a cooperative launch was refused once: stay on the other kernels
     float* res_scratch;
     size_t res_floats;
     int* err_flag_dev;             // device view of err_flag_host
@@ -886,17 +887,28 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     const bool forced_other = (a->flags & (MLB_FWD_FORCE_TILE | MLB_FWD_FORCE_CLUSTER)) != 0 || a->rows_per_group != 0;
     if ((a->flags & MLB_FWD_FORCE_WIDE) && h->wslab_dev == nullptr)
         return fail("mlb_forward: the whole-grid kernel is not available for this model / device");
-    if (h->wslab_dev != nullptr && ((a->flags & MLB_FWD_FORCE_WIDE) || (!forced_other && a->n_rows <= 64))) {
+    if (h->wslab_dev != nullptr && ((a->flags & MLB_FWD_FORCE_WIDE) || (!forced_other && !h->wide_disabled && a->n_rows <= 64))) {
         p.n_tiles = 1;
+        bool wide_ok = true;
         for (int row0 = 0; row0 < a->n_rows; row0 += 32) {
             p.row_base = row0;
             const unsigned base = h->wide_bar_count;
             h->wide_bar_count += (unsigned)mlb_wide_barriers(h->ops, d.n_ops) * (unsigned)(d.linear_size / 8);
             cudaError_t ew = mlb_wide_launch(p, h->wslab_dev, h->wslab_off, h->wide_xg, h->wide_bar, base, st);
-            if (ew != cudaSuccess) return fail(std::string("loco_forward_wide_kernel launch: ") + cudaGetErrorString(ew));
+            if (ew != cudaSuccess) {
+                h->wide_bar_count = base;  // nothing ran: the device counter did not move
+                if ((a->flags & MLB_FWD_FORCE_WIDE) || row0 > 0)
+                    return fail(std::string("loco_forward_wide_kernel launch: ") + cudaGetErrorString(ew));
+                // e.g. no cooperative launch under this context (MPS / partitioned SMs): use the other kernels from now on
+                cudaGetLastError();
+                wide_ok = false;
+                break;
+            }
             g_launches++;
         }
-        return 0;
+        if (wide_ok) return 0;
+        h->wide_disabled = true;
+        p.row_base = 0;
     }
 
     // ---- small batches: 8-CTA cluster per 16 detections (forward_small.cu) when that finishes sooner than row tiles.

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
     float* part = ring + (size_t)WNST * L * WC;         // [S][WC][R] partial sums
     float* outs = part + WPART;                         // [R][OUT_LD]
     float* cen = outs + R * OUT_LD;                     // [R][4]
-    uint64_t* wfull = reinterpret_cast<uint64_t*>(cen + R * 4);  // [WNST]
+    float* sstab = cen + R * 4;                         // [n_ops][32]: folded-BN scale[16] | shift-or-bias[16] of this CTA's columns
+    uint64_t* wfull = reinterpret_cast<uint64_t*>(sstab + MLB_MAX_OPS * 32);  // [WNST]
     uint64_t* gfull = wfull + WNST;                     // exchange-tile arrival
 
     unsigned long long* marks = (tid == 0 && (cta == 0 || cta == 64) && g_wide_marks != nullptr) ? g_wide_marks + (cta ? 128 : 0) : nullptr;
@@ -78,6 +79,18 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
         mbar_fence_init();
     }
     for (int i = tid; i < R * OUT_LD; i += WNT) outs[i] = 0.f;
+    // every layer's epilogue constants for this CTA's columns, fetched once up front (an L2 round trip per layer otherwise)
+    for (int i = tid; i < p.n_ops * 32; i += WNT) {
+        const mlb_op& op = p.ops[i >> 5];
+        const int j = i & 15, shift = (i >> 4) & 1;
+        float v = 0.f;
+        if (op.type == MLB_OP_GEMM) {
+            if (j < WC) v = __ldg(p.blob + (shift ? op.shift_off : op.scale_off) + cta * WC + j);
+        } else if (shift && j < op.N) {
+            v = __ldg(p.blob + op.shift_off + j);
+        }
+        sstab[i] = v;
+    }
     __syncthreads();
 
     // ---- weight stream.  Item = one [Kpad][8] slab: every GEMM op contributes the CTA's column slab; on CTA 0 (which
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
             wmark(marks, 3 + 4 * g);
             const bool last_gemm = g + 1 == n_gemm;
             if (epi) {
-                v = fmaf(v, __ldg(p.blob + op.scale_off + gcol), __ldg(p.blob + op.shift_off + gcol));
+                v = fmaf(v, sstab[oi * 32 + ec], sstab[oi * 32 + 16 + ec]);
                 if (op.flags & MLB_F_RELU) v = fmaxf(v, 0.f);
                 if ((op.flags & MLB_F_DROPOUT) && (p.flags & MLB_FWD_DROPOUT)) {
                     bool keep;
@@ -183,10 +196,8 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
             // ---- grid barrier, then pull the complete tile back (TMA bulk copy, L2 -> shared)
             __syncthreads();
             bar_target += gridDim.x;
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(ex.bar, 1u);
-            }
+            if (tid == 0)  // release-add: orders the CTA's exchange stores (observed through the barrier above) before the arrival
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ex.bar) : "memory");
             if (last_gemm && cta != 0) return;  // heads / decode / stores run on CTA 0 only
             if (tid == 0) {
                 unsigned spins = 0;
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
             for (int sub = 0; sub * WC < op.N; ++sub) {
                 const float v = slab_block(op.K);
                 const int o = sub * WC + ec;
-                if (epi && o < op.N) outs[er * OUT_LD + op.out_col + o] = v + __ldg(p.blob + op.shift_off + o);
+                if (epi && o < op.N) outs[er * OUT_LD + op.out_col + o] = v + sstab[oi * 32 + 16 + o];
                 __syncthreads();  // `part` is rewritten by the next slab
             }
             wmark(marks, 2 + 4 * g);
@@ -239,7 +250,7 @@ __global__ void wide_pack_kernel(const float* __restrict__ wt, float* __restrict
 
 template <int R>
 static size_t wide_smem(int L) {
-    return ((size_t)L * R + (size_t)WNST * L * WC + (size_t)WPART + (size_t)R * OUT_LD + (size_t)R * 4) * sizeof(float) +
+    return ((size_t)L * R + (size_t)WNST * L * WC + (size_t)WPART + (size_t)R * OUT_LD + (size_t)R * 4 + (size_t)MLB_MAX_OPS * 32) * sizeof(float) +
            (WNST + 1) * sizeof(uint64_t);
 }
 
