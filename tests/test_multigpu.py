@@ -41,7 +41,7 @@ def _worker(rank, world, port, n_total, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_total', [4096 * 2, 1001])
+@pytest.mark.parametrize('n_total', [4096 * 2, 1001, 40])
 def test_two_gpu_gather(n_total):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -54,7 +54,7 @@ def test_two_gpu_gather(n_total):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=300) for _ in range(2))
+    got = dict(q.get(timeout=150) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
