@@ -9,7 +9,7 @@ for B in [int(v) for v in (sys.argv[1:] or ['1', '8', '16', '32'])]:
     x = torch.from_numpy(synthetic.make_keypoints(B, seed=1)).cuda()
     res = []
     for kern in ('wide', 'cluster', 'tile'):
-        if kern == 'wide' and B > 32:
+        if kern == 'wide' and B > 64:
             res.append('wide n/a')
             continue
         kw = dict(kk=synthetic.KITTI_K, kind=L_.IN_KPS, kernel=kern)
