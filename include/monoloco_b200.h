@@ -245,6 +245,12 @@ uint64_t mlb_launch_count(void);
  * math done, [4+4i] CTA synchronised, [5+4i] activation tile rewritten; [2+4n] heads done, [3+4n] rows stored. */
 int mlb_debug_fwd_marks(void* dev_buf);
 
+/* tensor-core feasibility probe (tools/probe_tc.py; not on the product path): D[128,128] = A[128,K] . W[128,K]^T on
+ * tcgen05.mma kind::tf32 with every fp32 operand split into two TF32 terms.  mode 0: a_hi.w_hi only; 1: the three products
+ * into one TMEM accumulator; 2: the cross terms a_lo.w_hi + a_hi.w_lo into a second accumulator (out_cross).  K % 32 == 0. */
+int mlb_probe_tf32x3(const float* A_dev, const float* W_dev, int K, int mode, float* out_main_dev, float* out_cross_dev,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

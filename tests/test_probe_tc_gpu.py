@@ -1,0 +1,27 @@
+"""Experimental tensor-core probe (csrc/probe_tc.cu): not part of the product path; runs only with MLB_EXPERIMENTAL=1."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('MLB_EXPERIMENTAL') != '1',
+                                                  reason="experimental tcgen05 probe: set MLB_EXPERIMENTAL=1")]
+
+
+def test_tf32x3_probe_close_to_fp64():
+    from tools.probe_tc import run
+    rng = np.random.RandomState(1)
+    K = 256
+    A = rng.standard_normal((128, K)).astype(np.float32)
+    W = (rng.standard_normal((128, K)) / np.sqrt(K)).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    scale = np.abs(ref).max()
+    m0, _ = run(A, W, 0)
+    assert np.abs(m0 - ref).max() / scale < 5e-3          # plain TF32: ~1e-3
+    m2, c2 = run(A, W, 2)
+    assert np.abs(m2 + c2 - ref).max() / scale < 5e-6     # error-compensated: fp32-class
