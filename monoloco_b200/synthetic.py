@@ -122,3 +122,25 @@ def make_labels(n, stereo=False, seed=0):
     if stereo:
         cols.append((rng.uniform(0, 1, n) > 0.5).astype(np.float64))
     return np.stack(cols, axis=1).astype(np.float32)
+
+
+def make_joints_json(path, n_train=157, n_val=61, stereo=False, seed=5):
+    """A small joints file in the reference's format (prep/preprocess_kitti.py output): X[:,0] carries the row id so a
+    loader's batches reveal the sampling order."""
+    rng = np.random.RandomState(seed)
+    dic = {'version': 'synthetic-1'}
+    for phase, n in (('train', n_train), ('val', n_val)):
+        X = rng.uniform(-3, 3, size=(n, 68 if stereo else 34))
+        X[:, 0] = np.arange(n)
+        Y = rng.uniform(0.5, 30, size=(n, 11 if stereo else 10))
+        kps = rng.uniform(0, 1000, size=(n, 3, 17))
+        clst = {}
+        for name, lo, hi in (('10', 0, 10), ('20', 10, 20), ('30', 20, 30), ('>30', 30, 1e9)):
+            sel = [i for i in range(n) if lo <= Y[i, 3] < hi]
+            clst[name] = {'X': X[sel].tolist(), 'Y': Y[sel].tolist()}
+        dic[phase] = {'X': X.tolist(), 'Y': Y.tolist(), 'names': ['%06d.png' % i for i in range(n)], 'kps': kps.tolist(),
+                      'clst': clst}
+    import json
+    with open(path, 'w') as f:
+        json.dump(dic, f)
+    return dic

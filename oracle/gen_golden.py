@@ -270,12 +270,39 @@ def ref_api():
     print('api', len(boxes), len(boxes2), sorted(post.keys()))
 
 
+def ref_dataset_order():
+    """Batches of the reference's `DataLoader(KeypointsDataset(...), batch_size=bs, shuffle=True)` (trainer.py:102-103)
+    under torch.manual_seed: row ids per batch for two epochs of train and one of val, plus cluster sizes."""
+    import tempfile
+    from torch.utils.data import DataLoader
+    from monoloco.train.datasets import KeypointsDataset
+    path = os.path.join(tempfile.mkdtemp(), 'joints.json')
+    synthetic.make_joints_json(path)
+    out = {'seed': 11, 'bs': 32, 'joints_seed': 5}
+    torch.manual_seed(out['seed'])
+    loaders = {ph: DataLoader(KeypointsDataset(path, phase=ph), batch_size=out['bs'], shuffle=True) for ph in ('train', 'val')}
+    order = []
+    for epoch in range(2):
+        for ph in ('train', 'val'):
+            ids = []
+            for inputs, labels, names, kps in loaders[ph]:
+                ids.append([int(v) for v in inputs[:, 0].tolist()])
+                assert [int(nm[:6]) for nm in names] == ids[-1] and kps.shape[1:] == (3, 17)
+            order.append({'epoch': epoch, 'phase': ph, 'batches': ids})
+    out['order'] = order
+    ds = KeypointsDataset(path, phase='val')
+    out['clusters'] = {k: int(ds.get_cluster_annotations(k)[2]) for k in ('10', '20', '30', '>30')}
+    out['x_sum'] = float(ds.inputs_all.double().sum())
+    out['version'] = ds.get_version()
+    with open(os.path.join(OUT, 'ref_dataset_order.json'), 'w') as f:
+        json.dump(out, f)
+    print('ref_dataset_order.json', len(order), 'passes')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    kat_preprocess()
-    ref_forward()
-    ref_loco_forward()
-    ref_losses()
-    ref_epistemic()
-    ref_api()
+    steps = {'kat': kat_preprocess, 'forward': ref_forward, 'loco': ref_loco_forward, 'losses': ref_losses,
+             'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order}
+    for name in (sys.argv[1:] or list(steps)):   # python oracle/gen_golden.py [step ...]
+        steps[name]()
     print('done')

@@ -74,3 +74,30 @@ def test_train_then_predict_stereo(tmp_path):
     dic = net.forward(left, v['K'][0].tolist(), right)
     assert dic['xyzd'].shape[0] >= 10 and dic['aux'].shape[1] == 1
     assert ((dic['aux'] >= 0) & (dic['aux'] <= 1)).all() and np.isfinite(dic['d'].numpy()).all()
+
+
+def test_device_loader_feeds_fused_training_loop(tmp_path):
+    """N4 + A12 + N1 together: device-resident dataset -> one-launch train step -> fused clip + Adam (3 launches / batch),
+    every row seen exactly once per epoch, no per-batch host->device copy."""
+    from monoloco_b200 import synthetic
+    from monoloco_b200.network.architectures import LocoModel
+    from monoloco_b200.train import DeviceLoader, KeypointsDataset, FusedClipAdam, train_step
+    path = str(tmp_path / 'joints.json')
+    synthetic.make_joints_json(path, n_train=300, n_val=40, seed=3)
+    ds = KeypointsDataset(path, 'train')
+    loader = DeviceLoader(ds, batch_size=128, shuffle=True, device='cuda')
+    torch.manual_seed(0)
+    model = LocoModel(34, 9, linear_size=256, p_dropout=0.2, num_stage=2).cuda().train()
+    params = list(model.parameters())
+    opt = FusedClipAdam(params, lr=1e-3, max_norm=3, clip_params=params)
+    tasks = ('d', 'x', 'y', 'h', 'w', 'l', 'ori')
+    for epoch in range(2):
+        seen = []
+        for inputs, labels, names, kps in loader:
+            assert inputs.is_cuda and labels.is_cuda and kps.is_cuda and names is None
+            assert inputs.shape[1] == 34 and labels.shape[1] == 10 and kps.shape[1:] == (3, 17)
+            seen += [int(v) for v in inputs[:, 0].tolist()]
+            loss, vals, out = train_step(model, inputs, labels, tasks)
+            opt.step()
+            assert torch.isfinite(loss) and out.shape == (inputs.shape[0], 9)
+        assert sorted(seen) == list(range(300)) and len(loader) == 3
