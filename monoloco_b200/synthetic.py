@@ -144,3 +144,28 @@ def make_joints_json(path, n_train=157, n_val=61, stereo=False, seed=5):
     with open(path, 'w') as f:
         json.dump(dic, f)
     return dic
+
+
+def make_kitti_case(net, n=7, seed=0):
+    """Arguments of `save_txts(path, boxes, all_outputs, params, net, cat)` (eval/generate_kitti.py:119-147) for one image
+    with n detections: float32 tensors shaped like `Loco.forward`'s dictionary entries, python lists elsewhere."""
+    import torch
+    rng = np.random.RandomState(seed)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))  # noqa: E731
+    boxes = [[float(v) for v in np.round(rng.uniform(0, 1200, 4), 2)] + [float(rng.uniform(0.1, 1.0))] for _ in range(n)]
+    cat = [float(v) for v in rng.choice([0.0, 0.05, 0.3, 1.0], size=n)]
+    d = rng.uniform(3, 60, size=(n, 1))
+    xyz = rng.uniform(-1, 1, size=(n, 3)) * d
+    bi, epi = rng.uniform(0.1, 5, size=(n, 1)), rng.uniform(0, 1, size=n)
+    kk = [[718.3351, 0., 600.3891], [0., 718.3351, 181.5122], [0., 0., 1.]]
+    tt = [float(v) for v in rng.uniform(-0.5, 0.5, 3)]
+    if net in ('monoloco_pp', 'monstereo'):
+        outs = [f32(np.concatenate([xyz, d], 1)), f32(bi), [0.] * n if seed % 2 else f32(epi),
+                (f32(rng.uniform(-3, 3, (n, 1))), f32(rng.uniform(-3, 3, (n, 1)))),
+                f32(rng.uniform(1.4, 2, (n, 1))), f32(rng.uniform(0.4, 0.9, (n, 1))), f32(rng.uniform(0.4, 1.2, (n, 1)))]
+    else:
+        centers = f32(np.concatenate([rng.uniform(-1, 1, (n, 2)), np.ones((n, 1))], 1))
+        zzs = [float(v) for v in rng.uniform(3, 60, n)]
+        first = [[float(v) for v in row] for row in xyz] if net == 'baseline' else f32(d)
+        outs = [first, f32(bi), f32(epi), zzs, centers]
+    return boxes, outs, [kk, tt], cat

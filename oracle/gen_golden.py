@@ -299,10 +299,34 @@ def ref_dataset_order():
     print('ref_dataset_order.json', len(order), 'passes')
 
 
+def ref_kitti_txt():
+    """Text of the reference's `save_txts` (eval/generate_kitti.py:202-253) for every `net` branch on synthetic detections.
+    monoloco.eval asserts a data/logs directory at import time (eval_kitti.py:48), so the import runs from a scratch cwd."""
+    import tempfile
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.makedirs(os.path.join(tmp, 'data', 'logs'))
+    os.chdir(tmp)
+    try:
+        from monoloco.eval.generate_kitti import save_txts
+    finally:
+        os.chdir(cwd)
+    out = {}
+    for i, (net, n) in enumerate((('monoloco_pp', 7), ('monstereo', 5), ('monoloco', 6), ('geometric', 6), ('baseline', 4),
+                                  ('monoloco_pp', 0), ('monoloco_pp', 33))):
+        boxes, outs, params, cat = synthetic.make_kitti_case(net, n, seed=i)
+        path = os.path.join(tmp, 'out_%d.txt' % i)
+        save_txts(path, boxes, outs, params, net=net, cat=cat)
+        out['%d:%s:%d' % (i, net, n)] = open(path).read()
+    with open(os.path.join(OUT, 'ref_kitti_txt.json'), 'w') as f:
+        json.dump(out, f)
+    print('ref_kitti_txt.json', len(out), 'files')
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     steps = {'kat': kat_preprocess, 'forward': ref_forward, 'loco': ref_loco_forward, 'losses': ref_losses,
-             'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order}
+             'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order, 'kitti': ref_kitti_txt}
     for name in (sys.argv[1:] or list(steps)):   # python oracle/gen_golden.py [step ...]
         steps[name]()
     print('done')
