@@ -10,7 +10,6 @@ Differences that are deliberate and documented:
     reseeded generator (equal in distribution, not sample-for-sample);
   * there is no CPU mode: `device=None` selects the current CUDA device.
 """
-import math
 from collections import defaultdict
 
 import torch

@@ -10,7 +10,6 @@ import os
 import numpy as np
 import torch
 
-from .. import _lib as L_
 from ..engine import preprocess_device
 
 Sx, Sy = 7.2, 5.4  # nuScenes sensor size in mm (process.py:21-22)
