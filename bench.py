@@ -372,9 +372,9 @@ def main():
                                   "peak_source": "measured in-run by mlb_probe_ffma (pure FFMA kernel)",
                                   "algorithmic_flops": flops}},
         }
-        if not args.no_extras:
+        if not args.no_extras and world == 1:
             line["extras"] = extras(eng, sd, dev)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N = 1 only
             x = np.ascontiguousarray(synthetic.make_inputs(B, 34, seed=0))
             rate, reps, med = cpu_reference_rate(sd, x)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
