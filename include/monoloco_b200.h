@@ -250,6 +250,12 @@ int mlb_debug_fwd_marks(void* dev_buf);
  * into one TMEM accumulator; 2: the cross terms a_lo.w_hi + a_hi.w_lo into a second accumulator (out_cross).  K % 32 == 0. */
 int mlb_probe_tf32x3(const float* A_dev, const float* W_dev, int K, int mode, float* out_main_dev, float* out_cross_dev,
                      void* stream);
+/* the same error-compensated product for one whole layer, Y[B,N] = X[B,K] . W[N,K]^T (timing probe, not on the product
+ * path).  stages (bit mask): 1 = split X into TF32 hi/lo planes (x_planes_dev, 2*B*K floats), 2 = split W (w_planes_dev,
+ * 2*N*K floats), 4 = the tcgen05 GEMM from the planes (4-stage TMA ring, two TMEM accumulators).  B % 128 == 0,
+ * N % 256 == 0, K % 16 == 0. */
+int mlb_probe_tc_layer(const float* X_dev, const float* W_dev, float* Y_dev, int B, int N, int K, float* x_planes_dev,
+                       float* w_planes_dev, int stages, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,3 +25,9 @@ def test_tf32x3_probe_close_to_fp64():
     assert np.abs(m0 - ref).max() / scale < 5e-3          # plain TF32: ~1e-3
     m2, c2 = run(A, W, 2)
     assert np.abs(m2 + c2 - ref).max() / scale < 5e-6     # error-compensated: fp32-class
+
+
+def test_tc_layer_probe_close_to_fp64():
+    from tools.probe_tc import run_layer
+    us, err = run_layer(B=512, N=1024, K=1024, reps=3)
+    assert err < 5e-6 and us > 0

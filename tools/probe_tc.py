@@ -20,7 +20,43 @@ def run(A, W, mode):
     return main.cpu().numpy(), cross.cpu().numpy()
 
 
+def run_layer(B=4096, N=1024, K=1024, reps=20):
+    """One whole layer through mlb_probe_tc_layer: accuracy vs fp64 on a row sample, GEMM time by CUDA events."""
+    lib = L_.lib()
+    lib.mlb_probe_tc_layer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p]
+    rng = np.random.RandomState(2)
+    X = np.abs(rng.standard_normal((B, K))).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    x, w = torch.from_numpy(X).cuda(), torch.from_numpy(W).cuda()
+    y = torch.zeros((B, N), dtype=torch.float32, device='cuda')
+    xp = torch.empty(2 * B * K, dtype=torch.float32, device='cuda')
+    wp = torch.empty(2 * N * K, dtype=torch.float32, device='cuda')
+    call = lambda stages: L_.check(lib.mlb_probe_tc_layer(x.data_ptr(), w.data_ptr(), y.data_ptr(), B, N, K, xp.data_ptr(),  # noqa: E731
+                                                          wp.data_ptr(), stages, None), 'layer')
+    call(7)
+    torch.cuda.synchronize()
+    rows = rng.choice(B, 64, replace=False)
+    ref = X[rows].astype(np.float64) @ W.astype(np.float64).T
+    got = y[torch.from_numpy(rows).cuda()].cpu().numpy()
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    sg = float(np.abs((X[rows] @ W.T) - ref).max() / np.abs(ref).max())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        call(4)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    print('layer %dx%dx%d on tcgen05 (3xTF32, two accumulators): %.1f us = %.1f TFLOP/s fp32-equivalent; max err %.2e (numpy sgemm %.2e)'
+          % (B, N, K, us, 2.0 * B * N * K / us / 1e6, err, sg))
+    return us, err
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'layer':
+        run_layer(*[int(v) for v in sys.argv[2:]])
+        sys.exit(0)
     K = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     rng = np.random.RandomState(0)
     A = np.abs(rng.standard_normal((128, K))).astype(np.float32)          # post-ReLU-like activations (same sign: worst case
