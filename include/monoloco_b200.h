@@ -257,6 +257,15 @@ int mlb_probe_tf32x3(const float* A_dev, const float* W_dev, int K, int mode, fl
 int mlb_probe_tc_layer(const float* X_dev, const float* W_dev, float* Y_dev, int B, int N, int K, float* x_planes_dev,
                        float* w_planes_dev, int stages, void* stream);
 
+/* ---- EXPERIMENTAL tensor-core forward (csrc/forward_tc.cu; compile-checked only, never selected by mlb_forward):
+ * the same packed model (mlb_create arguments) on tcgen05.mma kind::tf32 with error-compensated operands.
+ * x_dev: pre-processed inputs [B, input_size]; out_raw_dev: raw network outputs [B, output_size] (decode: mlb_decode). */
+typedef struct mlb_tc* mlb_tc_handle;
+int mlb_tc_create(const mlb_model_desc* desc, const mlb_op* ops, const float* packed_host, size_t n_floats, int device,
+                  int max_rows, mlb_tc_handle* out);
+void mlb_tc_destroy(mlb_tc_handle h);
+int mlb_tc_forward(mlb_tc_handle h, const float* x_dev, int B, float* out_raw_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,8 @@ EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 
            'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
            'mlb_adam_clip_step',
            'mlb_probe_ffma',
-           'mlb_launch_count', 'mlb_debug_fwd_marks', 'mlb_probe_tf32x3', 'mlb_probe_tc_layer']
+           'mlb_launch_count', 'mlb_debug_fwd_marks', 'mlb_probe_tf32x3', 'mlb_probe_tc_layer',
+           'mlb_tc_create', 'mlb_tc_destroy', 'mlb_tc_forward']
 
 
 class MlbOp(C.Structure):

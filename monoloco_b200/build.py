@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmonoloco_b200.so')
-SOURCES = ['forward.cu', 'forward_small.cu', 'forward_wide.cu', 'train.cu', 'optim.cu', 'probe_tc.cu']
+SOURCES = ['forward.cu', 'forward_small.cu', 'forward_wide.cu', 'train.cu', 'optim.cu', 'probe_tc.cu', 'forward_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 

@@ -31,3 +31,11 @@ def test_tc_layer_probe_close_to_fp64():
     from tools.probe_tc import run_layer
     us, err = run_layer(B=512, N=1024, K=1024, reps=3)
     assert err < 5e-6 and us > 0
+
+
+@pytest.mark.parametrize('B,kind', [(300, 'loco'), (4096, 'loco'), (700, 'monoloco')])
+def test_tc_forward_parity(B, kind):
+    """The experimental tensor-core forward against the oracle under the product's parity rule."""
+    from tools.tc_forward import compare
+    ok, worst, t_tc, t_ff = compare(B, kind, reps=3)
+    assert ok, worst
