@@ -1,7 +1,8 @@
 """The hi / lo plane layout of the experimental tensor-core path (csrc/forward_tc.cu `tc_plane_off`, csrc/probe_tc.cu) must
 be the canonical K-major no-swizzle UMMA layout: checked on the host against CuTe's own
 `tile_to_shape(UMMA::Layout_K_INTER_Atom<tfloat32_t>, [rows x 16])` from the CUTLASS headers vendored in this image,
-together with the LBO / SBO the shared-memory descriptors are built with."""
+together with the LBO / SBO the shared-memory descriptors are built with, and the instruction / shared-memory
+descriptor bit patterns against `UMMA::make_instr_desc` / `UMMA::SmemDescriptor`."""
 import os
 import re
 import subprocess
@@ -15,6 +16,7 @@ SRC = r'''
 #include <cstdio>
 #include <cute/tensor.hpp>
 #include <cute/atom/mma_traits_sm100.hpp>
+#include <cute/arch/mma_sm100_desc.hpp>
 using namespace cute;
 template <int ROWS>
 int check() {
@@ -28,7 +30,17 @@ int check() {
            4 * ((int)layout(0, 4) - (int)layout(0, 0)), (int)cosize(layout));
     return bad;
 }
-int main() { return check<128>() + check<256>(); }
+int main() {
+    // descriptor encodings as CUTLASS builds them (cute/arch/mma_sm100_desc.hpp)
+    auto d1 = UMMA::make_instr_desc<tfloat32_t, tfloat32_t, float, 128, 256, UMMA::Major::K, UMMA::Major::K>();
+    auto d2 = UMMA::make_instr_desc<tfloat32_t, tfloat32_t, float, 128, 128, UMMA::Major::K, UMMA::Major::K>();
+    UMMA::SmemDescriptor s;
+    s.desc_ = 0;
+    s.start_address_ = (0x12340 >> 4) & 0x3FFF, s.leading_byte_offset_ = 2048 >> 4, s.stride_byte_offset_ = 128 >> 4, s.version_ = 1;
+    s.base_offset_ = 0, s.lbo_mode_ = 0, s.layout_type_ = 0;
+    printf("idesc256 %u idesc128 %u sdesc %llu\n", (uint32_t)d1.desc_, (uint32_t)d2.desc_, (unsigned long long)s.desc_);
+    return check<128>() + check<256>();
+}
 '''
 
 
@@ -55,6 +67,12 @@ def test_plane_layout_is_cute_canonical_k_major(tmp_path):
            for m in re.finditer(r'ROWS (\d+) bad (\d+) sbo (\d+) lbo (\d+) cosize (\d+)', out.stdout)}
     # (mismatches, SBO bytes, LBO bytes, floats per plane): forward_tc.cu TC_SBO / TC_LBO_A / TC_LBO_W, probe_tc.cu P_SBO / P_LBO
     assert got[128] == (0, 128, 128 * 16, 128 * 16) and got[256] == (0, 128, 256 * 16, 256 * 16)
+    # instruction / shared-memory descriptor bit patterns: the constants of forward_tc.cu / probe_tc.cu, re-stated
+    idesc = lambda m, n: (1 << 4) | (2 << 7) | (2 << 10) | ((n >> 3) << 17) | ((m >> 4) << 24)  # noqa: E731
+    sdesc = ((0x12340 & 0x3FFFF) >> 4) | (((2048 >> 4) & 0x3FFF) << 16) | (((128 >> 4) & 0x3FFF) << 32) | (1 << 46)
+    m = re.search(r'idesc256 (\d+) idesc128 (\d+) sdesc (\d+)', out.stdout)
+    assert (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (idesc(128, 256), idesc(128, 128), sdesc)
     cu = open(os.path.join(ROOT, 'monoloco_b200', 'csrc', 'forward_tc.cu')).read()
+    assert '(1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24)' in cu
     assert 'TC_LBO_A = TCM * 16, TC_LBO_W = TCN * 16, TC_SBO = 128' in cu
     assert '(size_t)(k_in_block >> 2) * tile_rows * 4 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4 + (k_in_block & 3)' in cu
