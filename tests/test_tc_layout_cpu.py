@@ -76,3 +76,22 @@ def test_plane_layout_is_cute_canonical_k_major(tmp_path):
     assert '(1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24)' in cu
     assert 'TC_LBO_A = TCM * 16, TC_LBO_W = TCN * 16, TC_SBO = 128' in cu
     assert '(size_t)(k_in_block >> 2) * tile_rows * 4 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4 + (k_in_block & 3)' in cu
+
+
+def test_tf32x3_emulation_meets_parity_rule():
+    """The arithmetic the experimental tensor-core path implements (tools/tf32x3_study.py: operands split into two TF32
+    terms, cross terms in their own accumulator, fp32 accumulators rounded once per k = 8 MMA -- even with the pessimistic
+    truncating adder) keeps the whole LocoModel forward inside the product's parity rule; plain TF32 does not."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from monoloco_b200 import synthetic
+    from oracle import loco_oracle as O
+    from tools.tf32x3_study import forward, mm_tf32x3_split, to_tf32
+    sd = {k: np.asarray(v) for k, v in synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0).items()}
+    x = O.preprocess_monoloco(synthetic.make_keypoints(24, seed=0), synthetic.KITTI_K)
+    ref = O.loco_model_forward(sd, x)
+    out = forward(sd, x, lambda a, w: mm_tf32x3_split(np.asarray(a, np.float32), w, 'rz'))
+    ok, worst = O.close(out, ref)
+    assert ok and worst < 1.0, worst
+    plain = forward(sd, x, lambda a, w: (to_tf32(np.asarray(a, np.float32)).astype(np.float64) @ to_tf32(w).astype(np.float64).T).astype(np.float32))
+    assert not O.close(plain, ref)[0]
