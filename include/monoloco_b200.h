@@ -20,11 +20,12 @@
 extern "C" {
 #endif
 
-#define MLB_ABI_VERSION 1
+#define MLB_ABI_VERSION 2
 #define MLB_MAX_OPS 32
 #define MLB_MAX_PEERS 8
 #define MLB_GATHER_LD 20   /* floats per gathered row: raw at [0,out), dec at [12,20) */
 #define MLB_GATHER_DEC 12
+#define MLB_GATHER_FLAG_STRIDE 32   /* uint32 between the per-rank completion flags (one 128-byte line each) */
 
 /* ---- layer program: one entry per Linear(+BN+ReLU+Dropout)(+residual) of architectures.py ---- */
 enum { MLB_OP_GEMM = 0, /* L-wide Linear, weights streamed through the TMA ring                    */
@@ -77,6 +78,10 @@ const char* mlb_last_error(void);
 int mlb_abi_version(void);
 /* number of SMs / resident CTAs the forward uses on this handle's device */
 int mlb_num_sms(mlb_handle h);
+/* device error word of this handle (mapped host memory; read it after a stream synchronisation): 0 = none,
+ * 1 = a TMA/mbarrier wait timed out, 3 = grid-barrier time-out (whole-grid kernel), 4 = fused all-gather: a peer
+ * rank did not signal its epoch within 20 s. */
+int mlb_device_error(mlb_handle h);
 
 /* ---- inference ---- */
 enum { MLB_IN_X = 0,          /* pre-processed network input [B, input_size] (nn.Module.forward)    */
@@ -114,8 +119,17 @@ typedef struct mlb_forward_args {
      * rank's and its NVLink peers' (pointers from mlb_ipc_open) -- at row gather_row0 + i.                  */
     float* gather[MLB_MAX_PEERS];
     int32_t n_gather;       /* 0 = off                                                              */
-    int32_t reserved0;
+    int32_t gather_rank;    /* index of this rank's own buffer in gather[] / gather_flags[]         */
     int64_t gather_row0;    /* first global row of this rank's shard                                */
+    /* device-side completion of the fused all-gather (no collective library in the data plane): when gather_epoch != 0
+     * the last CTA of the launch to finish its peer stores writes gather_epoch (st.release.sys) into slot gather_rank of
+     * EVERY rank's flag array, then spins (ld.acquire.sys) on this rank's own array until all n_gather slots have reached
+     * gather_epoch -- the kernel retires only when every shard has landed in this rank's buffer.  gather_flags[r] = rank
+     * r's flag array (MLB_GATHER_FLAG_STRIDE uint32 between slots, zero-initialised, in peer-mapped memory); epochs must
+     * increase by one per step on every rank.  gather_epoch == 0: no protocol, the caller synchronises the ranks.     */
+    uint32_t* gather_flags[MLB_MAX_PEERS];
+    uint32_t gather_epoch;
+    int32_t reserved0;
 } mlb_forward_args;
 
 /* Fused pre-process -> MLP -> heads -> decode on DEVICE buffers (replaces net.py:92-124 body:
@@ -133,10 +147,51 @@ int mlb_preprocess(const float* kps, int n_rows, const float kinv[9], float z_me
 /* monstereo arg-max filter (process.py:307-327): rows [n_left*n_right, out] viewed [n_left, n_right, out];
  * keeps, per left pose, every row whose last column >= the max over its right poses (ties kept, row-major
  * order).  Gathers raw (and dec / xyzc if non-NULL) rows into sel_*; writes the kept-row count to *n_sel_dev
- * and the kept flat row indices to sel_idx (capacity n_left*n_right).  Device buffers. */
+ * and the kept flat row indices to sel_idx (capacity n_left*n_right).  One warp per left pose, two launches (count,
+ * ordered scatter), no host synchronisation; cnt_scratch [n_left] int32 and best_scratch [n_left] fp32 are caller-owned
+ * device scratch.  Device buffers. */
 int mlb_stereo_filter(const float* raw, const float* dec, const float* xyzc, int n_left, int n_right, int out_size,
                       float* sel_raw, float* sel_dec, float* sel_xyzc, int32_t* sel_idx, int32_t* n_sel_dev,
-                      void* stream);
+                      int32_t* cnt_scratch, float* best_scratch, void* stream);
+
+/* ---- Loco.post_process for a BATCH of images on the device (net.py:164-248; utils/iou.py:6-29,44-64,87-101;
+ * utils/camera.py:10-29,82-96,161-177).  Detections / ground truths of all images are concatenated; det_off / gt_off are
+ * CSR offsets.  One CTA per image: bbox-centre / shoulder / head pixels (rounded half-even like Python round()), bbox-
+ * centre ray K^-1[u_c,v_c,1], xyz_from_distance(d, ray), conf = 0.035 * box_conf / (bi / |xyz|) in fp64, greedy IoU
+ * matching in decreasing box confidence (fp64, first maximum, each ground truth used once), the output order (matches
+ * first -- left to right by box x1 when `reorder` -- then the rest by index) and xyz_real of the matches.
+ * All pointers are device pointers. */
+typedef struct mlb_post_args {
+    int32_t n_img;
+    int32_t max_det;           /* largest number of detections in one image (shared-memory sizing)              */
+    int32_t max_gt;            /* largest number of ground-truth boxes in one image                              */
+    int32_t reorder;           /* net.py:185-186                                                                 */
+    double iou_min;            /* net.py:164 default 0.3                                                         */
+    const int32_t* det_off;    /* [n_img + 1]                                                                    */
+    const int32_t* gt_off;     /* [n_img + 1] or NULL (no ground truth)                                          */
+    const double* boxes;       /* [n_det][5] x1, y1, x2, y2, confidence (Python floats = fp64)                   */
+    const float* kps;          /* [n_det][3][17]                                                                 */
+    const float* kinv;         /* [n_img][9] K^-1 row-major, fp32                                                */
+    const float* dec;          /* [n_det][8] decoded network outputs (mlb_forward out_dec): d at 3, bi at 4      */
+    const double* gt_boxes;    /* [n_gt][4]                                                                      */
+    const double* gt_d;        /* [n_gt] ground-truth distances (dic_gt['ys'][j][3])                             */
+    float* xyz;                /* out [n_det][3] xyz_pred                                                        */
+    float* ray;                /* out [n_det][4] bbox-centre ray (x, y, z) and sqrt(1 + x^2 + y^2)               */
+    double* conf;              /* out [n_det]                                                                    */
+    int32_t* uv;               /* out [n_det][6] rounded centre, shoulder, head pixels                           */
+    int32_t* match_gt;         /* out [n_det] image-local index of the matched ground truth, or -1              */
+    int32_t* order;            /* out [n_det] per image: image-local detection index at every output position   */
+    int32_t* n_match;          /* out [n_img]                                                                    */
+    float* xyz_real;           /* out [n_det][3] xyz_from_distance(gt distance, ray) of matched detections       */
+} mlb_post_args;
+int mlb_post_process(const mlb_post_args* args, void* stream);
+
+/* KITTI label rows (eval/generate_kitti.py:202-253, nets monoloco_pp / monstereo): rows [n][15] fp64 =
+ * [alpha, x1, y1, x2, y2, h, w, l, x, y, z, ry, conf, bi, epi] with conf = conf_scale * box_conf / (bi / |xyz|)
+ * (conf_scale 0.035 monoloco_pp, 0.033 monstereo); the host only formats "%f".  boxes [n][5] fp64, raw [n][out_size],
+ * dec [n][8], epi [n] or NULL.  Device buffers. */
+int mlb_kitti_rows(int n, int out_size, double conf_scale, const double* boxes, const float* raw, const float* dec,
+                   const float* epi, double* rows, void* stream);
 
 /* decode only (process.py:231-278 / 330-360 on a raw tensor that did not come from mlb_forward):
  * raw [B, out_size] -> dec [B, 8] as in mlb_forward_args.out_dec.  Device buffers. */

@@ -5,11 +5,12 @@ import os
 
 from .build import LIB_PATH
 
-MLB_ABI_VERSION = 1
+MLB_ABI_VERSION = 2
 MLB_MAX_OPS = 32
 MLB_MAX_PEERS = 8
 GATHER_LD = 20
 GATHER_DEC = 12
+GATHER_FLAG_STRIDE = 32
 IPC_HANDLE_BYTES = 64
 OP_GEMM, OP_HEAD = 0, 1
 F_RELU, F_SAVE_RES, F_ADD_RES, F_DROPOUT, F_IN_XIN = 1, 2, 4, 8, 16
@@ -17,8 +18,8 @@ DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
 IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH, FWD_FORCE_WIDE = 1, 2, 4, 8, 16, 32, 64
 
-EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms',
-           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
+EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error',
+           'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_post_process', 'mlb_kitti_rows', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
            'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
            'mlb_adam_clip_step',
            'mlb_probe_ffma',
@@ -42,8 +43,17 @@ class MlbForwardArgs(C.Structure):
                 ('n_right', C.c_int32), ('rows_per_group', C.c_int32), ('kinv', C.c_float * 9), ('z_met', C.c_float),
                 ('x', C.c_void_p), ('x_right', C.c_void_p), ('out_raw', C.c_void_p), ('out_dec', C.c_void_p),
                 ('out_xyzc', C.c_void_p), ('out_x', C.c_void_p), ('drop_mask', C.c_void_p), ('drop_seed', C.c_uint64),
-                ('gather', C.c_void_p * MLB_MAX_PEERS), ('n_gather', C.c_int32), ('reserved0', C.c_int32),
-                ('gather_row0', C.c_int64)]
+                ('gather', C.c_void_p * MLB_MAX_PEERS), ('n_gather', C.c_int32), ('gather_rank', C.c_int32),
+                ('gather_row0', C.c_int64), ('gather_flags', C.c_void_p * MLB_MAX_PEERS), ('gather_epoch', C.c_uint32),
+                ('reserved0', C.c_int32)]
+
+
+class MlbPostArgs(C.Structure):
+    _fields_ = [('n_img', C.c_int32), ('max_det', C.c_int32), ('max_gt', C.c_int32), ('reorder', C.c_int32),
+                ('iou_min', C.c_double), ('det_off', C.c_void_p), ('gt_off', C.c_void_p), ('boxes', C.c_void_p),
+                ('kps', C.c_void_p), ('kinv', C.c_void_p), ('dec', C.c_void_p), ('gt_boxes', C.c_void_p),
+                ('gt_d', C.c_void_p), ('xyz', C.c_void_p), ('ray', C.c_void_p), ('conf', C.c_void_p), ('uv', C.c_void_p),
+                ('match_gt', C.c_void_p), ('order', C.c_void_p), ('n_match', C.c_void_p), ('xyz_real', C.c_void_p)]
 
 
 MLB_MAX_BLOCKS = 16
@@ -90,11 +100,15 @@ def lib():
     l.mlb_destroy.argtypes = [C.c_void_p]
     l.mlb_destroy.restype = None
     l.mlb_num_sms.argtypes = [C.c_void_p]
+    l.mlb_device_error.argtypes = [C.c_void_p]
     l.mlb_forward.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_forward_host.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_preprocess.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p, C.c_void_p]
     l.mlb_stereo_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.mlb_post_process.argtypes = [C.POINTER(MlbPostArgs), C.c_void_p]
+    l.mlb_kitti_rows.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
     l.mlb_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.mlb_laplace_std.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     l.mlb_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]

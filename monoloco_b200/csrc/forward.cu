@@ -409,40 +409,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
                 const int sr = tid, grp = sr >> 4, i = sr & 15;
                 const int r = grp * TM + i;
                 if (i < TM && r < rows_here) {
-                    const size_t grow = (size_t)row0 + r;
-                    const float* o = outs + sr * OUT_LD;
-                    for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
-                    float x, y, z, d, bi, yaw_p, yaw_o, aux;
-                    decode_row(p.decode_kind, p.out_size, o, x, y, z, d, bi, yaw_p, yaw_o, aux);
-                    if (p.out_dec != nullptr) {
-                        float4* dst = reinterpret_cast<float4*>(p.out_dec + grow * 8);
-                        dst[0] = make_float4(x, y, z, d);
-                        dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
-                    }
-                    // fused all-gather: the same row goes straight into every rank's gather buffer over NVLink
-                    for (int pg = 0; pg < p.n_gather; ++pg) {
-                        float* dst = p.gather[pg] + (size_t)(p.gather_row0 + (long long)grow) * MLB_GATHER_LD;
-                        for (int k = 0; k < p.out_size; ++k) dst[k] = o[k];
-                        reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
-                        reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
-                    }
-                    if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
-                        // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
-                        const float uc = cen[sr * 4 + 0], vc = cen[sr * 4 + 1];
-                        const float cx = uc * p.kinv[0] + vc * p.kinv[1] + p.kinv[2];
-                        const float cy = uc * p.kinv[3] + vc * p.kinv[4] + p.kinv[5];
-                        const float cz = uc * p.kinv[6] + vc * p.kinv[7] + p.kinv[8];
-                        const float den = sqrtf(__fadd_rn(__fadd_rn(1.f, __fmul_rn(cx, cx)), __fmul_rn(cy, cy)));
-                        const float px = __fdiv_rn(__fmul_rn(cx, d), den), py = __fdiv_rn(__fmul_rn(cy, d), den),
-                                    pz = __fdiv_rn(__fmul_rn(cz, d), den);
-                        const float nrm = sqrtf(px * px + py * py + pz * pz);
-                        *reinterpret_cast<float4*>(p.out_xyzc + grow * 4) = make_float4(px, py, pz, nrm);
-                    }
+                    store_row(p, (size_t)row0 + r, outs + sr * OUT_LD, cen + sr * 4);
                 }
             }
             consumer_sync(nthreads);
             fmark(marks, 3 + 4 * p.n_ops);
         }
+        if (tid == 0) gather_finish(p);  // fused all-gather: last CTA publishes this rank's epoch and waits for the peers'
         }  // active consumer warp
     }
 
@@ -450,6 +423,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) loco_forward_kernel(const __gr
     __syncthreads();
     if (res_tmem && warp == 0) tmem_dealloc(*tmem_slot, tmem_cols);
 }
+
+// a rank whose shard is empty still takes part in the completion protocol of the fused all-gather
+__global__ void gather_flag_only_kernel(const __grid_constant__ FwdParams p) { gather_finish(p); }
 
 // ------------------------------------------------------------------------------------------------
 // stand-alone pre-process (process.py:47-67) for callers that never run the network
@@ -480,65 +456,6 @@ __global__ void preprocess_kernel(const float* __restrict__ kps, int n_rows, flo
     if (lane < 17) {
         out_x[(size_t)row * 34 + 2 * lane] = (u * k0 + v * k1 + k2) * zm - cx;
         out_x[(size_t)row * 34 + 2 * lane + 1] = (u * k3 + v * k4 + k5) * zm - cy;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// monstereo arg-max filter (process.py:307-327), single CTA: per-left max, tie mask, ordered compaction
-// ------------------------------------------------------------------------------------------------
-__global__ void stereo_filter_kernel(const float* __restrict__ raw, const float* __restrict__ dec,
-                                     const float* __restrict__ xyzc, int n_left, int n_right, int out_size,
-                                     float* __restrict__ sel_raw, float* __restrict__ sel_dec, float* __restrict__ sel_xyzc,
-                                     int32_t* __restrict__ sel_idx, int32_t* __restrict__ n_sel) {
-    extern __shared__ int sm_cnt[];  // [n_left + 1] kept rows per left pose -> exclusive prefix
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int l = tid; l < n_left; l += nt) {
-        const float* v = raw + (size_t)l * n_right * out_size + (out_size - 1);
-        float best = v[0];
-        bool any_nan = best != best;
-        for (int r = 1; r < n_right; ++r) {
-            const float x = v[(size_t)r * out_size];
-            any_nan |= (x != x);
-            best = (x > best) ? x : best;
-        }
-        int cnt = 0;
-        if (!any_nan)
-            for (int r = 0; r < n_right; ++r) cnt += v[(size_t)r * out_size] >= best;
-        sm_cnt[l] = cnt;  // torch.max propagates NaN -> mask all False for that left pose
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int l = 0; l < n_left; ++l) {
-            const int cnt = sm_cnt[l];
-            sm_cnt[l] = run;
-            run += cnt;
-        }
-        sm_cnt[n_left] = run;
-        *n_sel = run;
-    }
-    __syncthreads();
-    for (int l = tid; l < n_left; l += nt) {
-        if (sm_cnt[l + 1] == sm_cnt[l]) continue;
-        const float* v = raw + (size_t)l * n_right * out_size + (out_size - 1);
-        float best = v[0];
-        for (int r = 1; r < n_right; ++r) {
-            const float x = v[(size_t)r * out_size];
-            best = (x > best) ? x : best;
-        }
-        int pos = sm_cnt[l];
-        for (int r = 0; r < n_right; ++r) {
-            if (v[(size_t)r * out_size] >= best) {
-                const size_t src = (size_t)l * n_right + r;
-                sel_idx[pos] = (int32_t)src;
-                for (int k = 0; k < out_size; ++k) sel_raw[(size_t)pos * out_size + k] = raw[src * out_size + k];
-                if (dec != nullptr && sel_dec != nullptr)
-                    for (int k = 0; k < 8; ++k) sel_dec[(size_t)pos * 8 + k] = dec[src * 8 + k];
-                if (xyzc != nullptr && sel_xyzc != nullptr)
-                    for (int k = 0; k < 4; ++k) sel_xyzc[(size_t)pos * 4 + k] = xyzc[src * 4 + k];
-                pos++;
-            }
-        }
     }
 }
 
@@ -654,6 +571,8 @@ struct mlb_model {
     bool wide_disabled;            // a cooperative launch was refused once: stay on the other kernels
     float* res_scratch;
     size_t res_floats;
+    unsigned* gather_done;         // monotonic count of CTAs that finished their peer stores (fused all-gather)
+    unsigned gather_done_count;    // host copy of the value it reaches after the launches issued so far
     int* err_flag_dev;             // device view of err_flag_host
     int* err_flag_host;            // mapped pinned host word: the host reads it after a sync without a copy
     // staging for mlb_forward_host
@@ -701,6 +620,7 @@ extern "C" int mlb_debug_fwd_marks(void* dev_buf) {
     return 0;
 }
 extern "C" int mlb_num_sms(mlb_handle h) { return h ? h->n_sms : 0; }
+extern "C" int mlb_device_error(mlb_handle h) { return h ? *reinterpret_cast<volatile int*>(h->err_flag_host) : -1; }
 
 static size_t fwd_smem_bytes(int L) {
     size_t fl = (size_t)L * MP + MP * OUT_LD + MP * 4 + (size_t)NSTAGE * KC * L;
@@ -769,6 +689,8 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
+    CU(cudaMalloc(&m->gather_done, sizeof(unsigned)));
+    CU(cudaMemset(m->gather_done, 0, sizeof(unsigned)));
     CU(cudaHostAlloc(reinterpret_cast<void**>(&m->err_flag_host), sizeof(int), cudaHostAllocMapped));
     *m->err_flag_host = 0;
     CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->err_flag_dev), m->err_flag_host, 0));
@@ -797,6 +719,7 @@ extern "C" void mlb_destroy(mlb_handle h) {
     cudaFree(h->wide_xg);
     cudaFree(h->wide_bar);
     cudaFree(h->res_scratch);
+    cudaFree(h->gather_done);
     cudaFreeHost(h->err_flag_host);
     cudaFree(h->st_in);
     cudaFree(h->st_in_r);
@@ -831,7 +754,29 @@ static cudaError_t launch_fwd(const FwdParams& p, int grid, int threads, size_t 
 extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream) {
     if (!h || !a) return fail("mlb_forward: null argument");
     if (a->n_rows < 0) return fail("mlb_forward: negative n_rows");
-    if (a->n_rows == 0) return 0;
+    if (a->n_gather < 0 || a->n_gather > MLB_MAX_PEERS) return fail("mlb_forward: n_gather out of range");
+    const bool sync_gather = a->n_gather > 0 && a->gather_epoch != 0;
+    if (sync_gather) {
+        if (a->gather_rank < 0 || a->gather_rank >= a->n_gather) return fail("mlb_forward: gather_rank out of range");
+        for (int i = 0; i < a->n_gather; ++i)
+            if (!a->gather_flags[i]) return fail("mlb_forward: null gather_flags pointer");
+    }
+    if (a->n_rows == 0) {
+        if (!sync_gather) return 0;
+        // empty shard: this rank still publishes its epoch and waits for the others
+        CU(cudaSetDevice(h->device));
+        FwdParams pe;
+        memset(&pe, 0, sizeof(pe));
+        pe.n_gather = a->n_gather, pe.gather_epoch = a->gather_epoch, pe.gather_rank = a->gather_rank;
+        for (int i = 0; i < a->n_gather; ++i) pe.gather_flags[i] = a->gather_flags[i];
+        pe.err_flag = h->err_flag_dev;
+        pe.gather_done = h->gather_done;
+        pe.gather_done_target = ++h->gather_done_count;
+        gather_flag_only_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(pe);
+        CU(cudaGetLastError());
+        g_launches++;
+        return 0;
+    }
     if (!a->x || !a->out_raw) return fail("mlb_forward: x and out_raw are required");
     const mlb_model_desc& d = h->desc;
     if (a->input_kind == MLB_IN_KPS && d.input_size != 34) return fail("mlb_forward: MLB_IN_KPS needs a 34-d model");
@@ -874,13 +819,22 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     p.p_drop = d.p_dropout;
     p.res_scratch = h->res_scratch;
     p.err_flag = h->err_flag_dev;
-    if (a->n_gather < 0 || a->n_gather > MLB_MAX_PEERS) return fail("mlb_forward: n_gather out of range");
     p.n_gather = a->n_gather;
     p.gather_row0 = a->gather_row0;
     for (int i = 0; i < a->n_gather; ++i) {
         if (!a->gather[i]) return fail("mlb_forward: null gather pointer");
         p.gather[i] = a->gather[i];
+        p.gather_flags[i] = sync_gather ? a->gather_flags[i] : nullptr;
     }
+    p.gather_rank = a->gather_rank;
+    p.gather_done = h->gather_done;
+    p.gather_epoch = 0;  // set, together with the arrival target, on the launch that completes the batch
+    auto arm_gather = [&](unsigned arrivals) {
+        if (!sync_gather) return;
+        p.gather_epoch = a->gather_epoch;
+        h->gather_done_count += arrivals;
+        p.gather_done_target = h->gather_done_count;
+    };
 
     // ---- one image's worth of detections: the whole grid on one 32-row tile at a time (forward_wide.cu).  Measured 45 /
     // 60 us per 16- / 32-row tile against 177 us for a wave of clusters: ahead up to two tiles.
@@ -892,11 +846,16 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
         bool wide_ok = true;
         for (int row0 = 0; row0 < a->n_rows; row0 += 32) {
             p.row_base = row0;
+            const bool last_launch = row0 + 32 >= a->n_rows;
+            const unsigned done_before = h->gather_done_count;
+            if (last_launch) arm_gather(1u);
             const unsigned base = h->wide_bar_count;
             h->wide_bar_count += (unsigned)mlb_wide_barriers(h->ops, d.n_ops) * (unsigned)(d.linear_size / 8);
             cudaError_t ew = mlb_wide_launch(p, h->wslab_dev, h->wslab_off, h->wide_xg, h->wide_bar, base, st);
             if (ew != cudaSuccess) {
-                h->wide_bar_count = base;  // nothing ran: the device counter did not move
+                h->wide_bar_count = base;  // nothing ran: the device counters did not move
+                h->gather_done_count = done_before;
+                p.gather_epoch = 0;
                 if ((a->flags & MLB_FWD_FORCE_WIDE) || row0 > 0)
                     return fail(std::string("loco_forward_wide_kernel launch: ") + cudaGetErrorString(ew));
                 // e.g. no cooperative launch under this context (MPS / partitioned SMs): use the other kernels from now on
@@ -922,6 +881,7 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
         const double t_tile = (0.42 + 0.067 * tm0) * ((tiles0 + h->n_sms - 1) / h->n_sms);
         if ((a->flags & MLB_FWD_FORCE_CLUSTER) || (a->rows_per_group == 0 && t_small < t_tile)) {
             p.n_tiles = n_clusters;
+            arm_gather((unsigned)(n_clusters < conc ? n_clusters : conc));  // one arrival per cluster leader
             cudaError_t es = mlb_small_launch(p, h->slab_dev, h->slab_off, n_clusters < conc ? n_clusters : conc, st);
             if (es != cudaSuccess) return fail(std::string("loco_forward_cluster_kernel launch: ") + cudaGetErrorString(es));
             g_launches++;
@@ -947,6 +907,7 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
     if ((size_t)grid * 128 * 256 > h->res_floats) return fail("mlb_forward: residual scratch too small");
 
+    arm_gather((unsigned)grid);  // every CTA owns >= 1 tile and arrives once
     cudaError_t e;
     switch (tm) {
         case 8: e = launch_fwd<8>(p, grid, threads, smem, st); break;
@@ -1050,22 +1011,6 @@ extern "C" int mlb_preprocess(const float* kps, int n_rows, const float kinv[9],
     const int wpb = 8;
     preprocess_kernel<<<(n_rows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
         kps, n_rows, kinv[0], kinv[1], kinv[2], kinv[3], kinv[4], kinv[5], z_met != 0.f ? z_met : 10.f, zero_center, out_x);
-    CU(cudaGetLastError());
-    g_launches++;
-    return 0;
-}
-
-extern "C" int mlb_stereo_filter(const float* raw, const float* dec, const float* xyzc, int n_left, int n_right, int out_size,
-                                 float* sel_raw, float* sel_dec, float* sel_xyzc, int32_t* sel_idx, int32_t* n_sel_dev,
-                                 void* stream) {
-    if (!raw || !sel_raw || !sel_idx || !n_sel_dev || n_left < 1 || n_right < 1 || out_size < 1)
-        return fail("mlb_stereo_filter: bad argument");
-    const size_t smem = (size_t)(n_left + 1) * sizeof(int);
-    if (smem > 200 * 1024) return fail("mlb_stereo_filter: too many left poses for one CTA");
-    if (smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(stereo_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stereo_filter_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(raw, dec, xyzc, n_left, n_right, out_size, sel_raw, sel_dec,
-                                                                 sel_xyzc, sel_idx, n_sel_dev);
     CU(cudaGetLastError());
     g_launches++;
     return 0;

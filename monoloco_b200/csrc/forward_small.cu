@@ -333,37 +333,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256, 1)
         if (rank == 0) {
             __syncthreads();
             if (tid < rows_here) {
-                const int r = tid;
-                const size_t grow = (size_t)row0 + r;
-                const float* o = outs + r * OUT_LD;
-                for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
-                float x, y, z, d, bi, yaw_p, yaw_o, aux;
-                decode_row(p.decode_kind, p.out_size, o, x, y, z, d, bi, yaw_p, yaw_o, aux);
-                if (p.out_dec != nullptr) {
-                    float4* dst = reinterpret_cast<float4*>(p.out_dec + grow * 8);
-                    dst[0] = make_float4(x, y, z, d);
-                    dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
-                }
-                for (int pg = 0; pg < p.n_gather; ++pg) {
-                    float* dst = p.gather[pg] + (size_t)(p.gather_row0 + (long long)grow) * MLB_GATHER_LD;
-                    for (int k = 0; k < p.out_size; ++k) dst[k] = o[k];
-                    reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
-                    reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
-                }
-                if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
-                    const float uc = cen[r * 4 + 0], vc = cen[r * 4 + 1];
-                    const float cx = uc * p.kinv[0] + vc * p.kinv[1] + p.kinv[2];
-                    const float cy = uc * p.kinv[3] + vc * p.kinv[4] + p.kinv[5];
-                    const float cz = uc * p.kinv[6] + vc * p.kinv[7] + p.kinv[8];
-                    const float den = sqrtf(__fadd_rn(__fadd_rn(1.f, __fmul_rn(cx, cx)), __fmul_rn(cy, cy)));
-                    const float px = __fdiv_rn(__fmul_rn(cx, d), den), py = __fdiv_rn(__fmul_rn(cy, d), den),
-                                pz = __fdiv_rn(__fmul_rn(cz, d), den);
-                    *reinterpret_cast<float4*>(p.out_xyzc + grow * 4) = make_float4(px, py, pz, sqrtf(px * px + py * py + pz * pz));
-                }
+                store_row(p, (size_t)row0 + tid, outs + tid * OUT_LD, cen + tid * 4);
             }
             __syncthreads();
         }
     }
+    if (rank == 0 && tid == 0) gather_finish(p);  // fused all-gather: one arrival per cluster leader
     cluster_arrive();
     cluster_wait();  // no CTA exits while a peer may still address its shared memory
 }

@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(WNT, 1) loco_forward_wide_kernel(const __grid_
     __syncthreads();
     wmark(marks, 2 + 4 * n_gemm);
     if (tid < rows_here) store_row(p, (size_t)row0 + tid, outs + tid * OUT_LD, cen + tid * 4);
+    if (p.n_gather) {
+        __syncthreads();
+        if (tid == 0) gather_finish(p);  // CTA 0 is the only storing CTA of this kernel
+    }
     wmark(marks, 3 + 4 * n_gemm);
 }
 

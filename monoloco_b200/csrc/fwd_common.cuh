@@ -28,7 +28,53 @@ struct FwdParams {
     float* gather[MLB_MAX_PEERS];
     int n_gather;
     long long gather_row0;
+    // device-side completion of the fused all-gather (mlb_forward_args.gather_epoch != 0)
+    unsigned* gather_flags[MLB_MAX_PEERS];  // rank r's flag array (peer-mapped)
+    unsigned gather_epoch;                  // 0: no protocol in this launch
+    int gather_rank;
+    unsigned* gather_done;                  // this device's monotonic "CTA finished its peer stores" counter
+    unsigned gather_done_target;            // its value once every storing CTA of this launch has arrived
 };
+
+enum { ERR_GATHER_TIMEOUT = 4 };
+
+// Called by ONE thread of every CTA that stored gather rows, after a CTA barrier that follows those stores (each storing
+// thread has executed __threadfence_system() after its last store).  The last CTA to arrive publishes this rank's epoch
+// into every rank's flag array (release at system scope: cumulativity orders all CTAs' peer stores before the flag) and
+// then waits until every rank's epoch has reached this rank's own array -- the kernel retires only when the whole
+// gathered buffer is complete here.  Bounded by %globaltimer (20 s): a dead peer raises the error flag instead of hanging.
+__device__ __forceinline__ void gather_finish(const FwdParams& p) {
+    if (p.n_gather == 0 || p.gather_epoch == 0) return;
+    __threadfence();
+    const unsigned prev = atomicAdd(p.gather_done, 1u);
+    if (prev + 1u != p.gather_done_target) return;
+    __threadfence_system();
+    for (int r = 0; r < p.n_gather; ++r) {
+        unsigned* f = p.gather_flags[r] + (size_t)p.gather_rank * MLB_GATHER_FLAG_STRIDE;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(p.gather_epoch) : "memory");
+    }
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned* mine = p.gather_flags[p.gather_rank];
+    for (int r = 0; r < p.n_gather; ++r) {
+        unsigned spins = 0;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + (size_t)r * MLB_GATHER_FLAG_STRIDE) : "memory");
+            if ((int)(v - p.gather_epoch) >= 0) break;
+            if ((++spins & 1023u) == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > 20000000000ull) {
+                    if (p.err_flag) *reinterpret_cast<volatile int*>(p.err_flag) = ERR_GATHER_TIMEOUT;
+                    __threadfence_system();
+                    return;
+                }
+            }
+        }
+    }
+    __threadfence_system();
+}
 
 // Laplace / spherical / orientation decode of one raw output row (process.py:231-278, 330-360; net.py:95-100).
 // Explicit __f*_rn intrinsics pin the reference's operation order (no FMA contraction).
@@ -146,6 +192,7 @@ __device__ __forceinline__ void store_row(const FwdParams& p, size_t grow, const
         reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
         reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
     }
+    if (p.n_gather) __threadfence_system();  // peer stores ordered before this CTA's arrival in gather_finish()
     if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
         // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
         const float uc = cen_row[0], vc = cen_row[1];

@@ -84,13 +84,20 @@ class LocoEngine:
         except Exception:  # interpreter shutdown
             pass
 
+    def check_error(self):
+        """Raise if a kernel of this engine reported a protocol time-out (call after a stream synchronisation)."""
+        err = self._lib.mlb_device_error(self._h)
+        if err:
+            raise RuntimeError("monoloco_b200: device error flag %d (1 TMA/mbarrier time-out, 3 grid barrier, "
+                               "4 fused all-gather peer time-out)" % err)
+
     # ---------------------------------------------------------------- forward on device tensors
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def forward(self, x, x_right=None, kk=None, kind=L_.IN_X, want_dec=True, want_xyzc=False, want_x=False,
                 zero_center=False, dropout=False, drop_mask=None, drop_seed=0, rows_per_group=0, res_tmem=None,
-                gather_ptrs=None, gather_row0=0, kernel=None):
+                gather_ptrs=None, gather_row0=0, gather_flags=None, gather_rank=0, gather_epoch=0, kernel=None):
         """x: float32 CUDA tensor ([B,in] | [B,3,17] | left [L,3,17]).  Returns dict of CUDA tensors."""
         assert x.is_cuda and x.dtype == torch.float32
         x = x.contiguous()
@@ -136,7 +143,12 @@ class LocoEngine:
             for i, ptr in enumerate(gather_ptrs):
                 a.gather[i] = ptr
             a.gather_row0 = int(gather_row0)
-        if B > 0:
+            if gather_flags:  # device-side completion protocol (include/monoloco_b200.h: gather_epoch)
+                for i, ptr in enumerate(gather_flags):
+                    a.gather_flags[i] = ptr
+                a.gather_rank = int(gather_rank)
+                a.gather_epoch = int(gather_epoch) & 0xFFFFFFFF
+        if B > 0 or (gather_ptrs and gather_flags and gather_epoch):  # an empty shard still signals its epoch
             L_.check(self._lib.mlb_forward(self._h, C.byref(a), self._stream()), 'mlb_forward')
         return out
 
@@ -177,21 +189,52 @@ class LocoEngine:
             L_.check(self._lib.mlb_forward_host(self._h, C.byref(a), self._stream()), 'mlb_forward_host')
         return out
 
-    def stereo_filter(self, raw, dec, n_left, n_right, xyzc=None):
-        """process.py:307-327 on device; returns (sel_raw, sel_dec, sel_idx[, sel_xyzc]) trimmed to the kept rows."""
+    def stereo_filter(self, raw, dec, n_left, n_right, xyzc=None, trim=True):
+        """process.py:307-327 on device (one warp per left pose, no host synchronisation inside).
+        trim=True : (sel_raw, sel_dec, sel_idx[, sel_xyzc]) CUDA tensors cut to the kept rows (reads the count: one sync);
+        trim=False: the full-capacity buffers plus the device count tensor `n_sel` as the last element, no sync."""
         B = n_left * n_right
         sel_raw = torch.empty_like(raw)
         sel_dec = torch.empty_like(dec) if dec is not None else None
         sel_xyzc = torch.empty_like(xyzc) if xyzc is not None else None
         sel_idx = torch.empty((B,), dtype=torch.int32, device=self.device)
-        n_sel = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        n_sel = torch.empty((1,), dtype=torch.int32, device=self.device)
+        cnt = torch.empty((n_left,), dtype=torch.int32, device=self.device)
+        best = torch.empty((n_left,), dtype=torch.float32, device=self.device)
         ptr = lambda t_: t_.data_ptr() if t_ is not None else None  # noqa: E731
         L_.check(self._lib.mlb_stereo_filter(raw.data_ptr(), ptr(dec), ptr(xyzc), n_left, n_right, raw.shape[1],
                                              sel_raw.data_ptr(), ptr(sel_dec), ptr(sel_xyzc), sel_idx.data_ptr(),
-                                             n_sel.data_ptr(), self._stream()), 'mlb_stereo_filter')
+                                             n_sel.data_ptr(), cnt.data_ptr(), best.data_ptr(), self._stream()),
+                 'mlb_stereo_filter')
+        if not trim:
+            res = (sel_raw, sel_dec, sel_idx)
+            return res + ((sel_xyzc,) if xyzc is not None else ()) + (n_sel,)
         n = int(n_sel.item())
         res = (sel_raw[:n], (sel_dec[:n] if dec is not None else None), sel_idx[:n])
         return res + (sel_xyzc[:n],) if xyzc is not None else res
+
+    def stereo_filter_host(self, raw, dec, xyzc, n_left, n_right):
+        """The filter for callers that want HOST tensors (Loco.forward): the count and the first n_left + 8 candidate rows
+        travel in one batch of asynchronous copies followed by ONE synchronisation; only when ties push the kept-row
+        count beyond that (process.py:321-326 keeps every tied row) is the remainder fetched."""
+        sel_raw, sel_dec, sel_idx, sel_xyzc, n_sel = self.stereo_filter(raw, dec, n_left, n_right, xyzc=xyzc, trim=False)
+        cap = min(n_left + 8, n_left * n_right)
+        st = getattr(self, '_sf_stage', None)
+        if st is None or st['raw'].shape[0] < cap or st['raw'].shape[1] != raw.shape[1]:
+            st = {'n': torch.empty((1,), dtype=torch.int32).pin_memory(),
+                  'raw': torch.empty((cap, raw.shape[1]), dtype=torch.float32).pin_memory(),
+                  'dec': torch.empty((cap, 8), dtype=torch.float32).pin_memory(),
+                  'xyzc': torch.empty((cap, 4), dtype=torch.float32).pin_memory()}
+            self._sf_stage = st
+        st['n'].copy_(n_sel, non_blocking=True)
+        st['raw'][:cap].copy_(sel_raw[:cap], non_blocking=True)
+        st['dec'][:cap].copy_(sel_dec[:cap], non_blocking=True)
+        st['xyzc'][:cap].copy_(sel_xyzc[:cap], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        n = int(st['n'][0])
+        if n <= cap:
+            return st['raw'][:n].clone(), st['dec'][:n].clone(), st['xyzc'][:n].clone()
+        return sel_raw[:n].cpu(), sel_dec[:n].cpu(), sel_xyzc[:n].cpu()
 
     def epistemic_std(self, x, n_dropout, n_samples=100, seed=1, kind=L_.IN_X, kk=None):
         """net.py:135-161: n_dropout stochastic forwards (top-level dropout on) -> (d, bi) -> Laplace sampling -> std.

@@ -83,10 +83,10 @@ class Loco:
                 else:
                     kps_r = kps[0:1, :].clone()  # net.py:115-116
                 out = eng.forward(kps, x_right=kps_r, kk=kk, kind=L_.IN_KPS_STEREO, want_xyzc=True)
-                raw, dec, _, xyzc = eng.stereo_filter(out['raw'], out['dec'], kps.shape[0], kps_r.shape[0],
-                                                      xyzc=out['xyzc'])  # process.py:307-327
+                raw, dec, xyzc = eng.stereo_filter_host(out['raw'], out['dec'], out['xyzc'], kps.shape[0],
+                                                        kps_r.shape[0])  # process.py:307-327, one sync
                 dic_out = dec_to_dict(raw, dec, stereo=True)
-                dic_out['xyz_c'] = xyzc[:, 0:3].cpu()
+                dic_out['xyz_c'] = xyzc[:, 0:3]
                 n_out = kps.shape[0]  # net.py:130: outputs is the clustered 3-D tensor -> number of left poses
                 inputs = None
             elif not self.epistemic and self.net != 'monoloco':

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 STRUCTS = {'mlb_op': 'MlbOp', 'mlb_model_desc': 'MlbModelDesc', 'mlb_forward_args': 'MlbForwardArgs',
-           'mlb_train_block': 'MlbTrainBlock', 'mlb_train_args': 'MlbTrainArgs'}
+           'mlb_train_block': 'MlbTrainBlock', 'mlb_train_args': 'MlbTrainArgs', 'mlb_post_args': 'MlbPostArgs'}
 
 
 def _c_layout(tmp_path):

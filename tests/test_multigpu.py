@@ -1,13 +1,25 @@
-"""GPU x2 (skipped on a single-GPU box): detections sharded over two ranks, outputs all-gathered either by NCCL or
-by the kernel's fused peer stores over NVLink; both must equal the oracle on the full batch."""
+"""GPU x2 / x4 (skipped when the box has fewer GPUs): detections sharded over the ranks, outputs all-gathered either by
+NCCL or by the kernel's fused peer stores + device-side flag protocol over NVLink; both must equal the oracle on the
+full batch, on every rank, for every kernel of the forward family:
+
+    8192 rows  -> row-tile kernel (4096 / 2048 rows per rank)        1001 -> cluster kernel, uneven shards
+    40 rows    -> whole-grid kernel, uneven shards at 4 ranks          1  -> ranks with an EMPTY shard still take part
+
+plus consecutive steps without host synchronisation (epoch protocol + the two alternating gather buffers) and the
+host-buffer end-to-end call.  One spawn per world size: every case runs inside the same process group."""
 import os
 import socket
+import traceback
 
 import numpy as np
 import pytest
 
 torch = pytest.importorskip('torch')
 pytestmark = pytest.mark.gpu
+
+CASES = (8192, 1001, 40, 1)
+STEP_ROWS = (1001, 40)   # consecutive-step cases (cluster / whole-grid kernels); 8192 is covered by bench.py's check
+N_STEPS = 4
 
 
 def _free_port():
@@ -18,56 +30,107 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_total, q):
-    import torch.distributed as dist
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
-    from monoloco_b200 import synthetic, engine, distributed as D
-    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
-    eng = engine.LocoEngine(sd, device=torch.device('cuda', rank))
-    kps = synthetic.make_keypoints(n_total, seed=5)
-    res = {}
-    for mode in ('nccl', 'fused'):
-        sh = D.ShardedLoco(eng, n_total, mode=mode)
-        local = torch.from_numpy(kps[sh.start:sh.stop]).cuda()
-        rows = sh.forward(local, synthetic.KITTI_K)
-        torch.cuda.synchronize()
-        res[mode] = rows.cpu().numpy().copy()
+def _worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+        from monoloco_b200 import synthetic, engine, distributed as D
+        sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+        eng = engine.LocoEngine(sd, device=torch.device('cuda', rank))
+        res = {}
+        for n_total in CASES:
+            kps = synthetic.make_keypoints(n_total, seed=5)
+            for mode in ('nccl', 'fused'):
+                sh = D.ShardedLoco(eng, n_total, mode=mode)
+                local = torch.from_numpy(kps[sh.start:sh.stop]).cuda()
+                rows = sh.forward(local, synthetic.KITTI_K)
+                torch.cuda.synchronize()
+                eng.check_error()
+                res[(n_total, mode)] = rows.cpu().numpy().copy()
+                if mode == 'fused':
+                    host = sh.forward_host(torch.from_numpy(kps[sh.start:sh.stop]).pin_memory(), synthetic.KITTI_K)
+                    res[(n_total, 'fused_host')] = host.numpy().copy()
+                dist.barrier()
+                sh.close()
+        # consecutive steps, different inputs, no host sync in between: results are cloned on the launching stream
+        for n_total in STEP_ROWS:
+            sh = D.ShardedLoco(eng, n_total, mode='fused')
+            keep = []
+            for s in range(N_STEPS):
+                kps = synthetic.make_keypoints(n_total, seed=100 + s)
+                local = torch.from_numpy(kps[sh.start:sh.stop]).cuda()
+                keep.append(sh.forward(local, synthetic.KITTI_K).clone())
+            torch.cuda.synchronize()
+            eng.check_error()
+            for s in range(N_STEPS):
+                res[(n_total, 'step%d' % s)] = keep[s].cpu().numpy().copy()
+            dist.barrier()
+            sh.close()
+        q.put((rank, 'ok', res))
         dist.barrier()
-        sh.close()
-    q.put((rank, res))
-    dist.barrier()
-    dist.destroy_process_group()
+        dist.destroy_process_group()
+    except Exception:  # report instead of leaving the peer in a collective until the time-out
+        q.put((rank, 'error', traceback.format_exc()))
 
 
-@pytest.mark.parametrize('n_total', [4096 * 2, 1001, 40])
-def test_two_gpu_gather(n_total):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     from oracle import loco_oracle as O
     from monoloco_b200 import synthetic, _lib as L_
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=150) for _ in range(2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    got = {}
+    try:
+        for _ in range(world):
+            rank, status, payload = q.get(timeout=240)
+            assert status == 'ok', "rank %d failed:\n%s" % (rank, payload)
+            got[rank] = payload
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
     sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
-    kps = synthetic.make_keypoints(n_total, seed=5)
-    ref_raw = O.loco_model_forward(sd, O.preprocess_monoloco(kps, synthetic.KITTI_K))
-    ref = O.extract_outputs(ref_raw)
-    for rank in (0, 1):
-        for mode in ('nccl', 'fused'):
-            rows = got[rank][mode]
-            assert rows.shape == (n_total, L_.GATHER_LD)
-            ok, worst = O.close(rows[:, :9], ref_raw)
-            assert ok, (rank, mode, worst)
-            ok, worst = O.close(rows[:, L_.GATHER_DEC:L_.GATHER_DEC + 4], ref['xyzd'], col_scale=False)
-            assert ok, (rank, mode, worst)
-    assert np.array_equal(got[0]['fused'], got[1]['fused']) and np.array_equal(got[0]['nccl'], got[0]['fused'])
+
+    def reference(n_total, seed):
+        kps = synthetic.make_keypoints(n_total, seed=seed)
+        raw = O.loco_model_forward(sd, O.preprocess_monoloco(kps, synthetic.KITTI_K))
+        return raw, O.extract_outputs(raw)
+
+    def check(rows, ref_raw, ref, what):
+        assert rows.shape == (ref_raw.shape[0], L_.GATHER_LD), what
+        ok, worst = O.close(rows[:, :9], ref_raw)
+        assert ok, (what, worst)
+        ok, worst = O.close(rows[:, L_.GATHER_DEC:L_.GATHER_DEC + 4], ref['xyzd'], col_scale=False)
+        assert ok, (what, worst)
+
+    for n_total in CASES:
+        ref_raw, ref = reference(n_total, 5)
+        for rank in range(world):
+            for mode in ('nccl', 'fused', 'fused_host'):
+                check(got[rank][(n_total, mode)], ref_raw, ref, (world, n_total, rank, mode))
+            # the gathered tensor is the same bytes on every rank and in both gather modes
+            assert np.array_equal(got[rank][(n_total, 'fused')], got[0][(n_total, 'fused')])
+            assert np.array_equal(got[rank][(n_total, 'fused')], got[rank][(n_total, 'fused_host')])
+        assert np.array_equal(got[0][(n_total, 'nccl')], got[0][(n_total, 'fused')])
+    for n_total in STEP_ROWS:
+        for s in range(N_STEPS):
+            ref_raw, ref = reference(n_total, 100 + s)
+            for rank in range(world):
+                check(got[rank][(n_total, 'step%d' % s)], ref_raw, ref, (world, n_total, rank, 'step', s))
+
+
+def test_two_gpu_gather():
+    _run(2)
+
+
+def test_four_gpu_gather():
+    _run(4)
