@@ -42,6 +42,14 @@ class _FusedModel(nn.Module):
     _engine = None
     _engine_key = None
 
+    def __getstate__(self):
+        # the engine is a ctypes handle to device memory: never copied or pickled (copy.deepcopy(model) for a best-model
+        # snapshot, torch.save(model)); the copy rebuilds its own engine lazily on first eval forward
+        state = self.__dict__.copy()
+        state.pop('_engine', None)
+        state.pop('_engine_key', None)
+        return state
+
     def _state_key(self):
         return tuple((id(t), t._version) for t in self.state_dict(keep_vars=True).values())
 

@@ -40,6 +40,7 @@ class _Workspace:
         self.max_rows = max_rows
         self.blocks = _blocks_of(model)
         self.lambda_cache = {}
+        self.generation = 0   # bumped by every launch that overwrites the saved activations (forward / train_step)
         L_.check(self.lib.mlb_train_create(device.index if device.index is not None else torch.cuda.current_device(),
                                            max_rows, model.stereo_size, model.linear_size, len(self.blocks),
                                            C.byref(self.h)), 'mlb_train_create')
@@ -145,12 +146,22 @@ class _FusedTrainFn(torch.autograd.Function):
         a, blocks = _fill(model, ws, x, out, drop_seed=seed, drop_mask=drop_mask)
         L_.check(ws.lib.mlb_train_forward(ws.h, C.byref(a), blocks, _stream(x.device)), 'mlb_train_forward')
         _bump_batches_tracked(model)
+        ws.generation += 1
         ctx.model, ctx.ws, ctx.x, ctx.seed, ctx.drop_mask, ctx.out = model, ws, x, seed, drop_mask, out
+        ctx.generation = ws.generation
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         model, ws, x = ctx.model, ctx.ws, ctx.x
+        if ws.generation != ctx.generation:
+            # the saved activations (Z / A / batch statistics) live in the per-model workspace, one set at a time: a later
+            # train-mode forward or train_step() has overwritten the ones this graph needs
+            raise RuntimeError(
+                "monoloco_b200: backward through a train-mode forward whose saved activations were overwritten by a later "
+                "train-mode forward of the same model (micro-batch accumulation, (loss1 + loss2).backward(), a no_grad "
+                "train-mode forward in between).  Call backward() before the next train-mode forward, or use "
+                "train_step(..., accumulate=True) per micro-batch.")
         grads = {n: torch.empty_like(p) for n, p in model.named_parameters()}
         g_out = g_out.float().contiguous()
         a, blocks = _fill(model, ws, x, ctx.out, grads=grads, g_out=g_out, drop_seed=ctx.seed, drop_mask=ctx.drop_mask,
@@ -159,11 +170,26 @@ class _FusedTrainFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads[n] for n, _ in model.named_parameters())
 
 
+def _next_drop_seed(device):
+    """Seed of the in-kernel dropout RNG for one step, taken from the device's default CUDA generator the way the
+    reference's CUDA nn.Dropout consumes it: (initial seed, philox offset) hashed, offset advanced on the HOST (no kernel,
+    no synchronisation).  The global CPU generator is never touched, so the DataLoader permutations that follow a
+    `torch.manual_seed(s)` stay identical to the reference's in every epoch; `torch.manual_seed` re-seeds the
+    CUDA generators too, so runs stay reproducible."""
+    import hashlib
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed0, off = int(gen.initial_seed()), int(gen.get_offset())
+    gen.set_offset(off + 4)   # philox offsets move in multiples of 4
+    mix = hashlib.blake2b(seed0.to_bytes(8, 'little', signed=seed0 < 0) + off.to_bytes(8, 'little'), digest_size=8).digest()
+    return int.from_bytes(mix, 'little') >> 2
+
+
 def fused_train_forward(model, x, drop_mask=None, seed=None):
     """LocoModel.forward in train mode (called by the module mirror)."""
     _check_model(model, x)
     if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())  # consumes torch's RNG stream like nn.Dropout would
+        seed = _next_drop_seed(x.device)
     params = [p for _, p in model.named_parameters()]
     return _FusedTrainFn.apply(x, model, seed, drop_mask, *params)
 
@@ -174,7 +200,7 @@ def train_step(model, x, labels, tasks, lambdas=None, log_sigmas=None, drop_mask
     exactly like `mt_loss(model(x), labels, phase='train')` followed by `loss.backward()`."""
     _check_model(model, x)
     if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = _next_drop_seed(x.device)
     tasks = tuple(tasks)
     lambdas = tuple(lambdas) if lambdas is not None else (1,) * len(tasks)
     ws = _workspace(model, x.shape[0], x.device)
@@ -195,6 +221,7 @@ def train_step(model, x, labels, tasks, lambdas=None, log_sigmas=None, drop_mask
     a, blocks = _fill(model, ws, x, out, grads=grads, labels=labels, tasks=tasks, scales=scales, loss_vals=loss_vals,
                       drop_seed=seed, drop_mask=drop_mask)
     L_.check(ws.lib.mlb_train_step(ws.h, C.byref(a), blocks, _stream(x.device)), 'mlb_train_step')
+    ws.generation += 1   # the workspace's saved activations now belong to this step
     _bump_batches_tracked(model)
     for n, p in model.named_parameters():
         p.grad = grads[n] if (p.grad is None or not accumulate) else p.grad + grads[n]

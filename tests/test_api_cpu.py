@@ -154,3 +154,25 @@ def test_activity_helpers(api):
     prob = [M.social_interactions(i, ref['centers'], ref['angles'], ref['dds'], stds=ref['stds']) for i in range(n)]
     det = [M.social_interactions(i, ref['centers'], ref['angles'], ref['dds'], stds=ref['stds'], n_samples=1) for i in range(n)]
     assert prob == ref['prob'] and det == ref['det']
+
+
+def test_model_copy_and_pickle_drop_the_engine_handle():
+    """copy.deepcopy(model) / torch.save(model) after an eval forward (best-model snapshots, EMA) must not trip
+    over the ctypes engine handle; the copy rebuilds its own engine lazily."""
+    import copy
+    import ctypes
+    import io
+    import torch
+    from monoloco_b200.network.architectures import LocoModel
+    m = LocoModel(34, 9, 128, num_stage=1)
+    object.__setattr__(m, '_engine', ctypes.c_void_p(1234))   # what engine() stores after the first eval forward
+    object.__setattr__(m, '_engine_key', ('k',))
+    c = copy.deepcopy(m)
+    assert c._engine is None and c._engine_key is None and '_engine' not in c.__dict__
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert r._engine is None and sorted(r.state_dict()) == sorted(m.state_dict())
+    assert m._engine.value == 1234   # the original keeps its handle

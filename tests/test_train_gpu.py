@@ -231,3 +231,59 @@ def test_fused_clip_adam_matches_torch():
         assert L_.lib().mlb_launch_count() - n0 == 2 and mine[0]._version == v0 + 1
         for a, b in zip(ref, mine):
             assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), float((a - b).abs().max())
+
+
+def test_fused_clip_adam_state_dict_round_trip():
+    """ADVICE r1: Adam's step count lives in optimizer state (bias correction survives state_dict -> load_state_dict);
+    more than one parameter group is refused."""
+    from monoloco_b200.train import FusedClipAdam
+    torch.manual_seed(1)
+    ps = [torch.randn(33, 7, device='cuda').requires_grad_(True), torch.randn(5, device='cuda').requires_grad_(True)]
+    ref = [p.detach().clone().requires_grad_(True) for p in ps]
+    o1, o_ref = FusedClipAdam(ps, lr=1e-2, max_norm=0.0), torch.optim.Adam(ref, lr=1e-2)
+    grads = [[torch.randn_like(p) for p in ps] for _ in range(4)]
+    for it in range(4):
+        if it == 2:   # checkpoint / resume in the middle
+            o2 = FusedClipAdam(ps, lr=1e-2, max_norm=0.0)
+            o2.load_state_dict(o1.state_dict())
+            o1 = o2
+        for p, r, g in zip(ps, ref, grads[it]):
+            p.grad, r.grad = g.clone(), g.clone()
+        o1.step()
+        o_ref.step()
+    for p, r in zip(ps, ref):
+        assert torch.allclose(p, r, rtol=2e-6, atol=2e-7)
+    assert int(o1.state[ps[0]]['step']) == 4
+    with pytest.raises(ValueError):
+        FusedClipAdam([{'params': [ps[0]]}, {'params': [ps[1]], 'lr': 1.0}])
+
+
+def test_backward_after_overwritten_activations_raises():
+    """the saved activations live in one per-model workspace; a backward whose activations were overwritten
+    by a later train-mode forward must raise instead of silently mixing batches."""
+    from monoloco_b200 import synthetic
+    from monoloco_b200.network.architectures import LocoModel
+    m = LocoModel(34, 9, 128, p_dropout=0.0, num_stage=1).cuda().train()
+    x1 = torch.from_numpy(synthetic.make_inputs(64, 34, seed=1)).cuda()
+    x2 = torch.from_numpy(synthetic.make_inputs(64, 34, seed=2)).cuda()
+    o1 = m(x1)
+    o2 = m(x2)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        o1.sum().backward()
+    o2.sum().backward()   # the most recent graph is intact
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_dropout_seeds_leave_the_cpu_generator_alone():
+    """per-step dropout seeds come from the CUDA generator's (seed, offset) like the reference's CUDA
+    nn.Dropout: the global CPU generator (DataLoader permutations) is untouched; torch.manual_seed reproduces them."""
+    from monoloco_b200.train.fused import _next_drop_seed
+    dev = torch.device('cuda', torch.cuda.current_device())
+    torch.manual_seed(7)
+    before = torch.get_rng_state()
+    a = [_next_drop_seed(dev) for _ in range(3)]
+    assert torch.equal(before, torch.get_rng_state())
+    torch.manual_seed(7)
+    assert [_next_drop_seed(dev) for _ in range(3)] == a
+    torch.manual_seed(8)
+    assert _next_drop_seed(dev) != a[0] and len(set(a)) == 3
