@@ -58,7 +58,8 @@ typedef struct mlb_model_desc {
     int32_t abi_version;  /* MLB_ABI_VERSION                                                        */
     int32_t input_size;   /* 34 mono | 68 stereo                     (net.py:45-58)                 */
     int32_t output_size;  /* raw output columns: 2 | 9 | 10                                         */
-    int32_t linear_size;  /* hidden width L: multiple of 128, <= 1024 (net.py:30, hyp_tuning.py:52) */
+    int32_t linear_size;  /* hidden width L (zero-padded by the packer): multiple of 128; <= 1024, or a     */
+                          /* multiple of 256 <= 2048 (tensor-core kernel only)  (net.py:30, hyp_tuning.py:52) */
     int32_t n_ops;
     int32_t decode_kind;  /* MLB_DECODE_*                                                           */
     float   p_dropout;    /* nn.Dropout p (architectures.py:46)                                     */
@@ -94,7 +95,8 @@ enum { MLB_FWD_ZERO_CENTER = 1, /* preprocess_monoloco(zero_center=True) (net.py
        MLB_FWD_FORCE_TILE    = 8,  /* always use the throughput kernel (one CTA per row tile)        */
        MLB_FWD_FORCE_CLUSTER = 16, /* always use the small-batch kernel (8-CTA cluster per 16 rows)  */
        MLB_FWD_RES_SCRATCH   = 32, /* stash the residual in the L2-resident global scratch instead   */
-       MLB_FWD_FORCE_WIDE    = 64  /* always use the whole-grid latency kernel (one launch / 32 rows)*/ };
+       MLB_FWD_FORCE_WIDE    = 64, /* always use the whole-grid latency kernel (one launch / 32 rows)*/
+       MLB_FWD_FORCE_TC      = 128 /* always use the tensor-core kernel (error-compensated TF32, 128-row tiles) */ };
 
 typedef struct mlb_forward_args {
     int32_t input_kind;     /* MLB_IN_*                                                             */
@@ -311,15 +313,6 @@ int mlb_probe_tf32x3(const float* A_dev, const float* W_dev, int K, int mode, fl
  * N % 256 == 0, K % 16 == 0. */
 int mlb_probe_tc_layer(const float* X_dev, const float* W_dev, float* Y_dev, int B, int N, int K, float* x_planes_dev,
                        float* w_planes_dev, int stages, void* stream);
-
-/* ---- EXPERIMENTAL tensor-core forward (csrc/forward_tc.cu; compile-checked only, never selected by mlb_forward):
- * the same packed model (mlb_create arguments) on tcgen05.mma kind::tf32 with error-compensated operands.
- * x_dev: pre-processed inputs [B, input_size]; out_raw_dev: raw network outputs [B, output_size] (decode: mlb_decode). */
-typedef struct mlb_tc* mlb_tc_handle;
-int mlb_tc_create(const mlb_model_desc* desc, const mlb_op* ops, const float* packed_host, size_t n_floats, int device,
-                  int max_rows, mlb_tc_handle* out);
-void mlb_tc_destroy(mlb_tc_handle h);
-int mlb_tc_forward(mlb_tc_handle h, const float* x_dev, int B, float* out_raw_dev, void* stream);
 
 #ifdef __cplusplus
 }

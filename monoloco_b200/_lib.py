@@ -17,6 +17,7 @@ F_RELU, F_SAVE_RES, F_ADD_RES, F_DROPOUT, F_IN_XIN = 1, 2, 4, 8, 16
 DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
 IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH, FWD_FORCE_WIDE = 1, 2, 4, 8, 16, 32, 64
+FWD_FORCE_TC = 128
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_post_process', 'mlb_kitti_rows', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
@@ -24,7 +25,7 @@ EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 
            'mlb_adam_clip_step',
            'mlb_probe_ffma',
            'mlb_launch_count', 'mlb_debug_fwd_marks', 'mlb_probe_tf32x3', 'mlb_probe_tc_layer',
-           'mlb_tc_create', 'mlb_tc_destroy', 'mlb_tc_forward']
+           ]
 
 
 class MlbOp(C.Structure):

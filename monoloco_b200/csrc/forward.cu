@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -544,6 +545,14 @@ size_t mlb_small_smem_bytes(int L);
 cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, long long* slab_off, cudaStream_t st);
 cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st);
 int mlb_small_max_clusters(int L);
+// forward_tc.cu
+struct mlb_tc_state;
+bool mlb_tc_supported(int L);
+mlb_tc_state* mlb_tc_prepare(const float* blob_dev, const mlb_op* ops, int n_ops, int L, cudaStream_t st, cudaError_t* err);
+cudaError_t mlb_tc_repack(mlb_tc_state* t, const float* blob_dev, const mlb_op* ops, int n_ops, int L, cudaStream_t st);
+void mlb_tc_free(mlb_tc_state* t);
+int mlb_tc_clusters(const mlb_tc_state* t, int n_rows);
+cudaError_t mlb_tc_launch(const mlb_tc_state* t, const FwdParams& p, cudaStream_t st);
 // forward_wide.cu
 size_t mlb_wide_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab_off);
 cudaError_t mlb_wide_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, const long long* slab_off, cudaStream_t st);
@@ -571,6 +580,9 @@ struct mlb_model {
     bool wide_disabled;            // a cooperative launch was refused once: stay on the other kernels
     float* res_scratch;
     size_t res_floats;
+    mlb_tc_state* tc;              // tensor-core kernel state (weight planes, cluster workspace), or null
+    bool ffma_ok;                  // the FFMA kernels fit this width (L <= 1024)
+    int tc_min_rows;               // batches of at least this many rows go to the tensor-core kernel
     unsigned* gather_done;         // monotonic count of CTAs that finished their peer stores (fused all-gather)
     unsigned gather_done_count;    // host copy of the value it reaches after the launches issued so far
     int* err_flag_dev;             // device view of err_flag_host
@@ -633,7 +645,10 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     if (desc->abi_version != MLB_ABI_VERSION) return fail("mlb_create: ABI version mismatch");
     if (desc->n_ops < 1 || desc->n_ops > MLB_MAX_OPS) return fail("mlb_create: n_ops out of range");
     const int L = desc->linear_size;
-    if (L < 128 || L > 1024 || (L % 128) != 0) return fail("mlb_create: linear_size must be a multiple of 128 in [128,1024]");
+    const bool ffma_ok = L >= 128 && L <= 1024 && (L % 128) == 0;
+    if (!ffma_ok && !mlb_tc_supported(L))
+        return fail("mlb_create: linear_size must be a multiple of 128 up to 1024 or a multiple of 256 up to 2048 "
+                    "(monoloco_b200.packing zero-pads other widths)");
     if (desc->input_size < 1 || desc->input_size > 68) return fail("mlb_create: input_size must be in [1,68]");
     if (desc->output_size < 1 || desc->output_size > OUT_LD) return fail("mlb_create: output_size must be in [1,16]");
     for (int i = 0; i < desc->n_ops; ++i) {
@@ -664,8 +679,21 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     m->device = device;
     m->n_sms = prop.multiProcessorCount;
     m->n_floats = n_floats;
+    m->ffma_ok = ffma_ok;
     CU(cudaMalloc(&m->blob_dev, n_floats * sizeof(float)));
     CU(cudaMemcpy(m->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
+    if (mlb_tc_supported(L)) {
+        cudaError_t et = cudaSuccess;
+        m->tc = mlb_tc_prepare(m->blob_dev, m->ops, desc->n_ops, L, 0, &et);
+        if (m->tc == nullptr) {
+            if (!ffma_ok) return fail(std::string("mlb_create: tensor-core kernel set-up: ") + cudaGetErrorString(et));
+            cudaGetLastError();  // the FFMA kernels cover this width: carry on without the tensor-core path
+        }
+        CU(cudaDeviceSynchronize());
+        // measured: one wave of 128-row tiles takes ~0.47 ms whatever the batch; the FFMA cluster / tile
+        // kernels pass that mark between 384 and 512 rows
+        m->tc_min_rows = getenv("MLB_TC_MIN_ROWS") ? atoi(getenv("MLB_TC_MIN_ROWS")) : 448;
+    }
     if (L == 1024) {
         size_t gemm_floats = 0;
         for (int i = 0; i < desc->n_ops; ++i)
@@ -676,7 +704,7 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
         m->small_conc = mlb_small_max_clusters(L);
         if (m->small_conc < 1) m->small_conc = 8;
     }
-    if (mlb_wide_supported(L, m->n_sms)) {
+    if (ffma_ok && mlb_wide_supported(L, m->n_sms)) {
         const size_t wf = mlb_wide_slab_floats(m->ops, desc->n_ops, L, m->wslab_off);
         CU(cudaMalloc(&m->wslab_dev, wf * sizeof(float)));
         CU(mlb_wide_pack(m->blob_dev, m->ops, desc->n_ops, L, m->wslab_dev, m->wslab_off, 0));
@@ -707,6 +735,7 @@ extern "C" int mlb_update_weights(mlb_handle h, const float* packed_host, size_t
         CU(mlb_small_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->slab_dev, h->slab_off, (cudaStream_t)stream));
     if (h->wslab_dev)
         CU(mlb_wide_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->wslab_dev, h->wslab_off, (cudaStream_t)stream));
+    if (h->tc) CU(mlb_tc_repack(h->tc, h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, (cudaStream_t)stream));
     return 0;
 }
 
@@ -720,6 +749,7 @@ extern "C" void mlb_destroy(mlb_handle h) {
     cudaFree(h->wide_bar);
     cudaFree(h->res_scratch);
     cudaFree(h->gather_done);
+    mlb_tc_free(h->tc);
     cudaFreeHost(h->err_flag_host);
     cudaFree(h->st_in);
     cudaFree(h->st_in_r);
@@ -835,6 +865,21 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
         h->gather_done_count += arrivals;
         p.gather_done_target = h->gather_done_count;
     };
+
+    // ---- large batches (and every batch of a model wider than the FFMA kernels cover): error-compensated TF32 on the
+    // tensor cores, persistent clusters over 128-row tiles (forward_tc.cu)
+    const bool forced_ffma = (a->flags & (MLB_FWD_FORCE_TILE | MLB_FWD_FORCE_CLUSTER | MLB_FWD_FORCE_WIDE)) != 0 || a->rows_per_group != 0;
+    if ((a->flags & MLB_FWD_FORCE_TC) && h->tc == nullptr)
+        return fail("mlb_forward: the tensor-core kernel is not available for this model (linear_size % 256 != 0)");
+    if (!h->ffma_ok && forced_ffma) return fail("mlb_forward: this model width runs on the tensor-core kernel only");
+    if (h->tc != nullptr && ((a->flags & MLB_FWD_FORCE_TC) || !h->ffma_ok || (!forced_ffma && a->n_rows >= h->tc_min_rows))) {
+        p.flags &= ~MLB_FWD_RES_TMEM;
+        arm_gather((unsigned)mlb_tc_clusters(h->tc, a->n_rows));  // one arrival per cluster leader
+        cudaError_t et = mlb_tc_launch(h->tc, p, st);
+        if (et != cudaSuccess) return fail(std::string("loco_forward_tc_kernel launch: ") + cudaGetErrorString(et));
+        g_launches++;
+        return 0;
+    }
 
     // ---- one image's worth of detections: the whole grid on one 32-row tile at a time (forward_wide.cu).  Measured 45 /
     // 60 us per 16- / 32-row tile against 177 us for a wave of clusters: ahead up to two tiles.

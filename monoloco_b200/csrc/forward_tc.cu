@@ -1,27 +1,37 @@
-// monoloco_b200 -- EXPERIMENTAL tensor-core forward (round-2 candidate; compile-checked only, never selected by mlb_forward).
+// monoloco_b200 -- throughput kernel on the 5th-gen tensor cores: the fp32 network as error-compensated TF32 products.
 //
-// The fp32 network on the 5th-gen tensor cores without leaving the 1e-5 parity rule (DESIGN.md "What comes next",
-// tools/tf32x3_study.py): every fp32 operand is split into two TF32 terms, a = a_hi + a_lo, and each layer product runs as
-// three tcgen05.mma kind::tf32 (a_hi.w_hi into a main TMEM accumulator, a_lo.w_hi + a_hi.w_lo into a second one).
+// The 1e-5 parity rule excludes plain TF32 / BF16.  Here every fp32 operand is split into two TF32 terms,
+// a = a_hi + a_lo (cvt.rna twice), and each layer product runs as THREE tcgen05.mma kind::tf32: a_hi.w_hi into a main TMEM
+// accumulator, a_lo.w_hi + a_hi.w_lo into a second one (the dropped a_lo.w_lo term is 2^-22 relative).  Measured on the
+// hardware (tools/probe_tc.py, tests/test_probe_tc_gpu.py): 2.6e-6 of max|ref| per 1024-deep layer against 6.8e-7 for an
+// fp32 SGEMM -- the whole network stays at ~0.5 of the parity tolerance (tests force this kernel on every fixture).
 //
-//   weights      re-packed once per model: per GEMM op  [4 column tiles][K/16 k blocks][hi | lo][256 x 16]  (canonical K-major
-//                no-swizzle UMMA layout: core matrix 8 rows x 16 B, SBO 128 B, LBO rows x 16 B)
-//   activations  between layers in the SAME layout,  [B/128 row tiles][1024/16][hi | lo][128 x 16], ping-pong in global / L2,
-//                so a pipeline stage is two 1-D TMA bulk copies (16 KB of X planes + 32 KB of W planes), no tensor maps
-//   kernel       cluster of 4 CTAs = one 128-row tile, CTA n owns output columns [256n, 256n + 256).  Per layer: warp 1 lane 0
-//                streams the stages through a 4-slot ring, warp 0 lane 0 issues 2 k-steps x 3 MMAs (M 128, N 256, K 8) per
-//                stage and releases it with tcgen05.commit; all 128 threads (thread = row) read main + cross back
-//                (tcgen05.ld), apply folded BN / ReLU / residual, and write the result straight into the next layer's hi / lo
-//                planes (+ an fp32 copy where a residual or a head needs it); barrier.cluster separates the layers.
-//   heads        a CUDA-core kernel (warp per 4 rows) on the fp32 copies; decode through the existing mlb_decode.
-// MC-dropout is not implemented on this path.
+// Replaces, like forward.cu, in ONE launch per detection batch (reference file:line):
+//   monoloco/network/process.py:25-67 (pre-process), architectures.py:48-71 / 88-102 / 135-145 (network),
+//   process.py:231-278, 330-360 + utils/camera.py:161-177, 202-237 (decode, xyz_from_distance).
+//
+//   weights      re-packed once per model: per GEMM op  [L/256 column tiles][K/16 k blocks][hi | lo][256 x 16]  (canonical
+//                K-major no-swizzle UMMA layout: core matrix 8 rows x 16 B, SBO 128 B, LBO rows x 16 B) -> a pipeline stage
+//                is two 1-D TMA bulk copies (16 KB of X planes + 32 KB of W planes), no tensor maps
+//   kernel       persistent thread-block clusters, L/256 CTAs each (4 at L = 1024).  A cluster owns a private workspace slot
+//                (input planes, two ping-pong activation plane sets, the fp32 residual: 2.6 MB, L2-resident for every
+//                cluster at once) and walks 128-row tiles.  CTA n owns output columns [256n, 256n + 256) of every layer.
+//   per tile     prologue: thread = row: pre-process the raw keypoints (process.py:47-67 / 25-44) straight into hi / lo planes
+//                per layer: warp 1 lane 0 streams the stages through a 4-slot ring, warp 0 lane 0 issues 2 k-steps x 3 MMAs
+//                (M 128, N 256, K 8) per stage and releases the stage with tcgen05.commit; all 128 threads (thread = row) read
+//                main + cross back (tcgen05.ld), apply folded BN / ReLU / dropout / residual and write the result straight
+//                into the next layer's hi / lo planes; narrow heads (w_aux, w_fin, MonolocoModel.w2) are accumulated on the
+//                CUDA cores from the same registers; barrier.cluster separates the layers
+//   tail         head partial sums -> CTA 0 through distributed shared memory -> decode_row -> stores (raw, decoded, xyz of
+//                the bbox-centre ray, fused all-gather peers), exactly the epilogue of the FFMA kernels (fwd_common.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
 
-#include "common.cuh"
+#include "fwd_common.cuh"
 
 namespace mlb {
 
@@ -30,24 +40,23 @@ constexpr uint32_t TC_A_PLANE = TCM * TCKB * 4, TC_W_PLANE = TCN * TCKB * 4;  //
 constexpr uint32_t TC_STAGE = 2 * TC_A_PLANE + 2 * TC_W_PLANE;                 // 48 KB
 constexpr uint32_t TC_LBO_A = TCM * 16, TC_LBO_W = TCN * 16, TC_SBO = 128;
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
-constexpr int TC_MAX_LAYERS = 16;
+constexpr int TC_MAX_CT = 8;       // column tiles = CTAs per cluster (L <= 2048)
+constexpr int TC_HW = 16;          // head output columns in total (output_size <= 16)
+constexpr size_t TC_RING_BYTES = (size_t)TCNST * TC_STAGE;
+constexpr size_t TC_SMEM_BYTES = TC_RING_BYTES + (size_t)TC_HW * TCN * sizeof(float);  // ring + this CTA's head-weight slice
 
-struct TcLayer {
-    const float* wplanes;  // [L/256][n_kb][hi|lo][256 x 16]
-    const float* scale;    // folded BatchNorm scale [L]
-    const float* shift;    // folded BatchNorm shift (+ bias) [L]
-    int n_kb;              // K / 16
-    int flags;             // MLB_F_RELU | MLB_F_SAVE_RES | MLB_F_ADD_RES
-    int head_buf;          // index of the fp32 buffer that keeps this layer's output for a head, or -1
-};
-
-struct TcParams {
-    TcLayer layer[TC_MAX_LAYERS];
-    int n_layers, L, rows_pad;
-    float* xplanes[2];   // [rows_pad/128][L/16][hi|lo][128 x 16]; [0] also holds the network input (n_kb of layer 0)
-    float* res_f32;      // [rows_pad][L] stage input kept for the residual add
-    float* head_f32[2];  // [rows_pad][L] outputs that feed a narrow head
-    int* err_flag;
+struct TcExtra {
+    const float* wplanes[MLB_MAX_OPS];  // per GEMM op: [L/256][n_kb][hi|lo][256 x 16]
+    int n_kb[MLB_MAX_OPS];              // K blocks of 16 (K zero-padded)
+    float* ws;                          // workspace, one slot per cluster
+    unsigned long long slot_floats;
+    int n_tiles;                        // 128-row tiles of this launch
+    // narrow heads: rows of all head ops concatenated (q = 0 .. n_head_rows-1)
+    int n_head_rows;
+    int head_src[TC_HW];                // op index of the GEMM whose output head row q reads
+    int head_col[TC_HW];                // raw output column of head row q
+    long long head_w[TC_HW];            // float offset of head row q's K weights in the blob
+    long long head_b[TC_HW];            // float offset of its bias
 };
 
 __device__ __forceinline__ float tc_tf32(float x) {
@@ -55,11 +64,13 @@ __device__ __forceinline__ float tc_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 [0,14), LBO >> 4 [16,30), SBO >> 4 [32,46),
+// version = 1 [46,48), layout type SWIZZLE_NONE [61,64)
 __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((TC_SBO >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+    d |= (uint64_t)1 << 46;
     return d;
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
@@ -79,25 +90,28 @@ __device__ __forceinline__ void tc_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t tc_cluster_id() {  // clusters are laid out along x: one cluster per blockIdx.x
+    return blockIdx.x;
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {  // 32 consecutive TMEM columns of this thread's lane
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // float offset of element (row r, k) inside one [tile_rows x 16] plane
 __device__ __forceinline__ size_t tc_plane_off(int r, int k_in_block, int tile_rows) {
     return (size_t)(k_in_block >> 2) * tile_rows * 4 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4 + (k_in_block & 3);
-}
-
-// network input [B][in_size] fp32 -> hi / lo planes with K padded to n_kb * 16, rows padded to rows_pad (zeros)
-__global__ void tc_pack_input_kernel(const float* __restrict__ x, float* __restrict__ planes, int B, int in_size, int n_kb, int rows_pad) {
-    const int K = n_kb * TCKB;
-    const size_t plane = (size_t)TCM * TCKB;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)rows_pad * K; i += (size_t)gridDim.x * blockDim.x) {
-        const int row = (int)(i / K), k = (int)(i % K);
-        const float v = (row < B && k < in_size) ? x[(size_t)row * in_size + k] : 0.f;
-        const float h = tc_tf32(v), l = tc_tf32(v - h);
-        float* blk = planes + ((size_t)(row / TCM) * n_kb + k / TCKB) * 2 * plane;
-        const size_t off = tc_plane_off(row % TCM, k % TCKB, TCM);
-        blk[off] = h;
-        blk[plane + off] = l;
-    }
 }
 
 // W^T [Kpad][L] (the packed blob's layout) -> W planes with K padded to n_kb * 16
@@ -115,148 +129,279 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wt, float* __re
     }
 }
 
-__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(128, 1) tc_forward_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TcExtra ex) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[TCNST], empty[TCNST], done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rb = blockIdx.x, nt = blockIdx.y, L = p.L;
+    const int nt = blockIdx.y, nct = gridDim.y, L = p.L;
+    float* hw = reinterpret_cast<float*>(smem_raw + TC_RING_BYTES);  // [TC_HW][256] head weights of this CTA's columns
+    float* hpart = reinterpret_cast<float*>(smem_raw);               // [nct][128][TC_HW] on CTA 0; aliases the idle ring
 
     if (tid == 0) {
         for (int s = 0; s < TCNST; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
         mbar_init(&done, 1);
         mbar_fence_init();
     }
+    for (int i = tid; i < TC_HW * TCN; i += 128) {
+        const int q = i / TCN, c = i % TCN;
+        hw[i] = q < ex.n_head_rows ? __ldg(p.blob + ex.head_w[q] + nt * TCN + c) : 0.f;
+    }
     if (warp == 0) tmem_alloc(&tmem_slot, 512);  // [0,256) main accumulator, [256,512) cross terms
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
+    tc_cluster_sync();  // every CTA of the cluster is resident before any remote shared-memory store can be issued
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    const size_t grow = (size_t)rb * TCM + tid;  // this thread's row in the epilogue
+
+    // this cluster's workspace slot
+    int first_gemm = 0;
+    while (p.ops[first_gemm].type != MLB_OP_GEMM) ++first_gemm;
+    const int n_kb0 = ex.n_kb[first_gemm];
+    const size_t plane = (size_t)TCM * TCKB;
+    float* slot = ex.ws + (size_t)tc_cluster_id() * ex.slot_floats;
+    float* xin = slot;                                   // [n_kb0][hi|lo][128 x 16]
+    float* xpl[2] = {xin + (size_t)n_kb0 * 2 * plane, xin + (size_t)n_kb0 * 2 * plane + (size_t)(L / TCKB) * 2 * plane};
+    float* res = xpl[1] + (size_t)(L / TCKB) * 2 * plane;  // [128][L] fp32
+
+    const float zm = p.z_met;
+    const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
+    const bool mc_drop = (p.flags & MLB_FWD_DROPOUT) != 0;
+    const float inv_keep = 1.0f / (1.0f - p.p_drop);
+    const uint32_t seed_mix = drop_seed_mix(p.drop_seed), thr = drop_threshold(p.p_drop);
 
     unsigned it_p = 0, it_m = 0;  // stages issued / consumed so far (producer lane, MMA lane)
-    int par = 0;                  // activation plane buffer the current layer reads
-    for (int g = 0; g < p.n_layers; ++g) {
-        const TcLayer& ly = p.layer[g];
-        if (warp == 1 && lane == 0) {
-            // ---- producer: this row tile's X planes and this column tile's W planes, 48 KB per stage
-            asm volatile("fence.proxy.async;" ::: "memory");  // the cluster peers' epilogue stores -> this thread's TMA reads
-            const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(p.xplanes[par]) + (size_t)rb * ly.n_kb * 2 * TC_A_PLANE;
-            const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(ly.wplanes) + (size_t)nt * ly.n_kb * 2 * TC_W_PLANE;
-            for (int kb = 0; kb < ly.n_kb; ++kb, ++it_p) {
-                const unsigned s = it_p % TCNST;
-                if (it_p >= TCNST) mbar_wait(&empty[s], ((it_p / TCNST) - 1) & 1, p.err_flag);
-                unsigned char* st = smem_raw + (size_t)s * TC_STAGE;
-                mbar_expect_tx(&full[s], TC_STAGE);
-                tma_bulk_g2s(st, xsrc + (size_t)kb * 2 * TC_A_PLANE, 2 * TC_A_PLANE, &full[s]);
-                tma_bulk_g2s(st + 2 * TC_A_PLANE, wsrc + (size_t)kb * 2 * TC_W_PLANE, 2 * TC_W_PLANE, &full[s]);
-            }
-        } else if (warp == 0 && lane == 0) {
-            // ---- MMA issuer
-            tmem_fence_after();
-            uint32_t main_acc = 0, cross_acc = 0;
-            for (int kb = 0; kb < ly.n_kb; ++kb, ++it_m) {
-                const unsigned s = it_m % TCNST;
-                mbar_wait(&full[s], (it_m / TCNST) & 1, p.err_flag);
-                tmem_fence_after();
-                const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE), a_lo = a_hi + TC_A_PLANE;
-                const uint32_t w_hi = a_hi + 2 * TC_A_PLANE, w_lo = w_hi + TC_W_PLANE;
-#pragma unroll
-                for (int j = 0; j < TCKB / 8; ++j) {
-                    const uint64_t ah = tc_desc(a_hi + 2 * j * TC_LBO_A, TC_LBO_A), al = tc_desc(a_lo + 2 * j * TC_LBO_A, TC_LBO_A);
-                    const uint64_t wh = tc_desc(w_hi + 2 * j * TC_LBO_W, TC_LBO_W), wl = tc_desc(w_lo + 2 * j * TC_LBO_W, TC_LBO_W);
-                    tc_mma(tmem + TCN, al, wh, cross_acc), cross_acc = 1;
-                    tc_mma(tmem + TCN, ah, wl, 1u);
-                    tc_mma(tmem, ah, wh, main_acc), main_acc = 1;
-                }
-                tc_commit(&empty[s]);
-            }
-            tc_commit(&done);
-        }
-        __syncwarp();
-        mbar_wait_backoff(&done, (uint32_t)(g & 1), p.err_flag);
-        tmem_fence_after();
+    unsigned n_done = 0;          // layers finished by this CTA (parity of `done`)
+    for (int rb = (int)tc_cluster_id(); rb < ex.n_tiles; rb += (int)gridDim.x) {
+        const int grow = rb * TCM + tid;  // this thread's detection
+        const bool live = grow < p.n_rows;
+        float cenrow[4] = {0.f, 0.f, 0.f, 0.f};
 
-        // ---- epilogue: thread = row; columns [256 nt, 256 nt + 256) in steps of 8 (= two 16-byte chunks of a k block)
-        float* nxt = p.xplanes[par ^ 1];
-        const bool relu = (ly.flags & MLB_F_RELU) != 0, add_res = (ly.flags & MLB_F_ADD_RES) != 0, save_res = (ly.flags & MLB_F_SAVE_RES) != 0;
-        const size_t plane = (size_t)TCM * TCKB;
-        for (int c0 = 0; c0 < TCN; c0 += 8) {
-            float m[8], c[8];
-            tmem_ld8(lane_base + (uint32_t)c0, m);
-            tmem_ld8(lane_base + (uint32_t)(TCN + c0), c);
-            const int col = nt * TCN + c0;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(ly.scale + col)), s1 = __ldg(reinterpret_cast<const float4*>(ly.scale + col + 4));
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(ly.shift + col)), t1 = __ldg(reinterpret_cast<const float4*>(ly.shift + col + 4));
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            float v[8];
+        // ------------------------------------------------------------ prologue: network input of my row -> hi / lo planes
+        // every CTA of the cluster evaluates its row (cheap); CTA nt writes k blocks nt, nt + nct, ...
+        {
+            float xr[KIN_MAX + 8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                v[j] = fmaf(m[j] + c[j], sc[j], sh[j]);
-                if (relu) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (add_res) {
-                const float4 r0 = *reinterpret_cast<const float4*>(p.res_f32 + grow * L + col);
-                const float4 r1 = *reinterpret_cast<const float4*>(p.res_f32 + grow * L + col + 4);
-                v[0] += r0.x, v[1] += r0.y, v[2] += r0.z, v[3] += r0.w, v[4] += r1.x, v[5] += r1.y, v[6] += r1.z, v[7] += r1.w;
-            }
-            if (save_res) {
-                *reinterpret_cast<float4*>(p.res_f32 + grow * L + col) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(p.res_f32 + grow * L + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (ly.head_buf >= 0) {
-                float* hb = p.head_f32[ly.head_buf] + grow * L + col;
-                *reinterpret_cast<float4*>(hb) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(hb + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            // next layer's A operand: output column `col` is its k index
-            float* blk = nxt + ((size_t)rb * (L / TCKB) + col / TCKB) * 2 * plane;
+            for (int k = 0; k < KIN_MAX + 8; ++k) xr[k] = 0.f;
+            if (live) {
+                if (p.input_kind == MLB_IN_X) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float4 h = make_float4(tc_tf32(v[4 * q]), tc_tf32(v[4 * q + 1]), tc_tf32(v[4 * q + 2]), tc_tf32(v[4 * q + 3]));
-                const float4 l = make_float4(tc_tf32(v[4 * q] - h.x), tc_tf32(v[4 * q + 1] - h.y), tc_tf32(v[4 * q + 2] - h.z),
-                                             tc_tf32(v[4 * q + 3] - h.w));
-                const size_t off = tc_plane_off(tid, (col % TCKB) + 4 * q, TCM);
-                *reinterpret_cast<float4*>(blk + off) = h;
-                *reinterpret_cast<float4*>(blk + plane + off) = l;
+                    for (int k = 0; k < KIN_MAX; ++k)
+                        if (k < p.in_size) xr[k] = __ldg(p.x + (size_t)grow * p.in_size + k);
+                } else {
+                    const bool stereo = p.input_kind == MLB_IN_KPS_STEREO;
+                    const float* kp = p.x + (size_t)(stereo ? grow / p.n_right : grow) * 51;
+                    const float* kr = stereo ? p.xr + (size_t)(grow % p.n_right) * 51 : nullptr;
+                    float umin = __ldg(kp), umax = umin, vmin = __ldg(kp + 17), vmax = vmin;
+                    for (int j = 1; j < 17; ++j) {
+                        const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
+                        umin = fminf(umin, u), umax = fmaxf(umax, u);
+                        vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+                    }
+                    const float uc = __fadd_rn(__fdiv_rn(__fsub_rn(umax, umin), 2.f), umin);  // camera.py:82-86
+                    const float vc = __fadd_rn(__fdiv_rn(__fsub_rn(vmax, vmin), 2.f), vmin);
+                    cenrow[0] = uc, cenrow[1] = vc;
+                    cenrow[2] = (uc * k0 + vc * k1 + k2) * zm;
+                    cenrow[3] = (uc * k3 + vc * k4 + k5) * zm;
+                    const bool zc = (p.flags & MLB_FWD_ZERO_CENTER) != 0;
+#pragma unroll
+                    for (int j = 0; j < 17; ++j) {
+                        const float u = __ldg(kp + j), v = __ldg(kp + 17 + j);
+                        float xl = (u * k0 + v * k1 + k2) * zm;  // camera.py:26-27, rows 0/1 of [u v 1] K^-T
+                        float yl = (u * k3 + v * k4 + k5) * zm;
+                        if (stereo) {
+                            const float ur = __ldg(kr + j), vr = __ldg(kr + 17 + j);
+                            xr[34 + 2 * j] = xl - (ur * k0 + vr * k1 + k2) * zm;  // process.py:41 cat(l, l - r)
+                            xr[35 + 2 * j] = yl - (ur * k3 + vr * k4 + k5) * zm;
+                        } else if (zc) {
+                            xl -= cenrow[2];  // process.py:61-62
+                            yl -= cenrow[3];
+                        }
+                        xr[2 * j] = xl, xr[2 * j + 1] = yl;
+                    }
+                }
+                if (nt == 0 && p.out_x != nullptr && p.input_kind != MLB_IN_X) {
+#pragma unroll
+                    for (int k = 0; k < KIN_MAX; ++k)
+                        if (k < p.in_size) p.out_x[(size_t)grow * p.in_size + k] = xr[k];
+                }
+            }
+#pragma unroll
+            for (int kb = 0; kb < (KIN_MAX + 8) / TCKB; ++kb) {
+                if (kb < n_kb0 && (kb % nct) == nt) {
+                    float* blk = xin + (size_t)kb * 2 * plane;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = make_float4(xr[kb * 16 + 4 * q], xr[kb * 16 + 4 * q + 1], xr[kb * 16 + 4 * q + 2], xr[kb * 16 + 4 * q + 3]);
+                        const float4 h = make_float4(tc_tf32(v.x), tc_tf32(v.y), tc_tf32(v.z), tc_tf32(v.w));
+                        const float4 l = make_float4(tc_tf32(v.x - h.x), tc_tf32(v.y - h.y), tc_tf32(v.z - h.z), tc_tf32(v.w - h.w));
+                        const size_t off = tc_plane_off(tid, 4 * q, TCM);
+                        *reinterpret_cast<float4*>(blk + off) = h;
+                        *reinterpret_cast<float4*>(blk + plane + off) = l;
+                    }
+                }
             }
         }
-        tmem_fence_before();
-        tc_cluster_sync();  // all four column tiles of this row tile are written; TMEM reads are complete
-        tmem_fence_after();
-        par ^= 1;
+        tc_cluster_sync();  // the input planes of this tile are complete (and the previous tile's tail is over everywhere)
+
+        float hacc[TC_HW];
+#pragma unroll
+        for (int q = 0; q < TC_HW; ++q) hacc[q] = 0.f;
+
+        int par = 0, site = 0, gi = 0;  // gi: GEMM ops done in this tile
+        for (int oi = 0; oi < p.n_ops; ++oi) {
+            const mlb_op& op = p.ops[oi];
+            if (op.type != MLB_OP_GEMM) continue;
+            const int n_kb = ex.n_kb[oi];
+            const float* xsrc_f = gi == 0 ? xin : xpl[par];
+            if (warp == 1 && lane == 0) {
+                // ---- producer: this row tile's X planes and this column tile's W planes, 48 KB per stage
+                asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy stores (planes, hpart) -> async-proxy TMA
+                const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(xsrc_f);
+                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(ex.wplanes[oi]) + (size_t)nt * n_kb * 2 * TC_W_PLANE;
+                for (int kb = 0; kb < n_kb; ++kb, ++it_p) {
+                    const unsigned s = it_p % TCNST;
+                    if (it_p >= TCNST) mbar_wait(&empty[s], ((it_p / TCNST) - 1) & 1, p.err_flag);
+                    unsigned char* st = smem_raw + (size_t)s * TC_STAGE;
+                    mbar_expect_tx(&full[s], TC_STAGE);
+                    tma_bulk_g2s(st, xsrc + (size_t)kb * 2 * TC_A_PLANE, 2 * TC_A_PLANE, &full[s]);
+                    tma_bulk_g2s(st + 2 * TC_A_PLANE, wsrc + (size_t)kb * 2 * TC_W_PLANE, 2 * TC_W_PLANE, &full[s]);
+                }
+            } else if (warp == 0 && lane == 0) {
+                // ---- MMA issuer
+                tmem_fence_after();
+                uint32_t main_acc = 0, cross_acc = 0;
+                for (int kb = 0; kb < n_kb; ++kb, ++it_m) {
+                    const unsigned s = it_m % TCNST;
+                    mbar_wait(&full[s], (it_m / TCNST) & 1, p.err_flag);
+                    tmem_fence_after();
+                    const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE), a_lo = a_hi + TC_A_PLANE;
+                    const uint32_t w_hi = a_hi + 2 * TC_A_PLANE, w_lo = w_hi + TC_W_PLANE;
+#pragma unroll
+                    for (int j = 0; j < TCKB / 8; ++j) {
+                        const uint64_t ah = tc_desc(a_hi + 2 * j * TC_LBO_A, TC_LBO_A), al = tc_desc(a_lo + 2 * j * TC_LBO_A, TC_LBO_A);
+                        const uint64_t wh = tc_desc(w_hi + 2 * j * TC_LBO_W, TC_LBO_W), wl = tc_desc(w_lo + 2 * j * TC_LBO_W, TC_LBO_W);
+                        tc_mma(tmem + TCN, al, wh, cross_acc), cross_acc = 1;
+                        tc_mma(tmem + TCN, ah, wl, 1u);
+                        tc_mma(tmem, ah, wh, main_acc), main_acc = 1;
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&done);
+            }
+            __syncwarp();
+            mbar_wait_backoff(&done, (uint32_t)(n_done & 1), p.err_flag);
+            ++n_done;
+            tmem_fence_after();
+
+            // ---- epilogue: thread = row; columns [256 nt, 256 nt + 256) in steps of 32
+            float* nxt = xpl[gi == 0 ? 0 : (par ^ 1)];
+            const bool relu = (op.flags & MLB_F_RELU) != 0, add_res = (op.flags & MLB_F_ADD_RES) != 0,
+                       save_res = (op.flags & MLB_F_SAVE_RES) != 0;
+            const bool drop = mc_drop && (op.flags & MLB_F_DROPOUT) != 0;
+            const uint32_t rm = drop_row_mix(seed_mix, (uint32_t)grow);
+            int q_lo = TC_HW, q_hi = 0;  // head rows fed by this layer's output
+            for (int q = 0; q < ex.n_head_rows; ++q)
+                if (ex.head_src[q] == oi) q_lo = min(q_lo, q), q_hi = max(q_hi, q + 1);
+            float* res_row = res + (size_t)tid * L + nt * TCN;
+            for (int c0 = 0; c0 < TCN; c0 += 32) {
+                float m[32], c[32];
+                tc_ld32(lane_base + (uint32_t)c0, m);
+                tc_ld32(lane_base + (uint32_t)(TCN + c0), c);
+                const int col = nt * TCN + c0;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + col + 4 * j4));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + col + 4 * j4));
+                    float v[4];
+                    v[0] = fmaf(m[4 * j4 + 0] + c[4 * j4 + 0], sc.x, sh.x);
+                    v[1] = fmaf(m[4 * j4 + 1] + c[4 * j4 + 1], sc.y, sh.y);
+                    v[2] = fmaf(m[4 * j4 + 2] + c[4 * j4 + 2], sc.z, sh.z);
+                    v[3] = fmaf(m[4 * j4 + 3] + c[4 * j4 + 3], sc.w, sh.w);
+                    if (relu) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                    }
+                    if (drop) {
+                        if (p.drop_mask != nullptr) {
+                            if (live) {
+                                const uint32_t mk = *reinterpret_cast<const uint32_t*>(p.drop_mask + ((size_t)site * p.n_rows + grow) * L + col + 4 * j4);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[e] = ((mk >> (8 * e)) & 0xFFu) ? v[e] * inv_keep : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                v[e] = drop_keep(rm, drop_col_hash((uint32_t)(col + 4 * j4 + e), (uint32_t)site), thr) ? v[e] * inv_keep : 0.f;
+                        }
+                    }
+                    if (add_res) {
+                        const float4 r = *reinterpret_cast<const float4*>(res_row + c0 + 4 * j4);
+                        v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
+                    }
+                    if (save_res) *reinterpret_cast<float4*>(res_row + c0 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (q_hi > q_lo) {  // narrow heads on this layer's output: partial dot products over my 256 columns
+#pragma unroll
+                        for (int q = 0; q < TC_HW; ++q) {
+                            if (q >= q_lo && q < q_hi) {
+                                const float4 w = *reinterpret_cast<const float4*>(hw + q * TCN + c0 + 4 * j4);
+                                hacc[q] = fmaf(v[3], w.w, fmaf(v[2], w.z, fmaf(v[1], w.y, fmaf(v[0], w.x, hacc[q]))));
+                            }
+                        }
+                    }
+                    // next layer's A operand: output column `col + 4 j4 ..` is its k index
+                    const int kcol = col + 4 * j4;
+                    float* blk = nxt + (size_t)(kcol / TCKB) * 2 * plane;
+                    const float4 h = make_float4(tc_tf32(v[0]), tc_tf32(v[1]), tc_tf32(v[2]), tc_tf32(v[3]));
+                    const float4 l = make_float4(tc_tf32(v[0] - h.x), tc_tf32(v[1] - h.y), tc_tf32(v[2] - h.z), tc_tf32(v[3] - h.w));
+                    const size_t off = tc_plane_off(tid, kcol % TCKB, TCM);
+                    *reinterpret_cast<float4*>(blk + off) = h;
+                    *reinterpret_cast<float4*>(blk + plane + off) = l;
+                }
+            }
+            if (op.flags & MLB_F_DROPOUT) site++;
+            tmem_fence_before();
+            tc_cluster_sync();  // all column tiles of this row tile are written; TMEM reads are complete
+            tmem_fence_after();
+            if (gi > 0) par ^= 1;
+            ++gi;
+        }
+
+        // ------------------------------------------------------------ tail: head partials -> CTA 0 -> decode + stores
+        {
+            const uint32_t local = smem_u32(hpart + ((size_t)nt * TCM + tid) * TC_HW);
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0u));
+#pragma unroll
+            for (int q4 = 0; q4 < TC_HW / 4; ++q4)
+                asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + 16u * q4), "f"(hacc[4 * q4]),
+                             "f"(hacc[4 * q4 + 1]), "f"(hacc[4 * q4 + 2]), "f"(hacc[4 * q4 + 3])
+                             : "memory");
+        }
+        tc_cluster_sync();
+        if (nt == 0 && live) {
+            float o[OUT_LD];
+#pragma unroll
+            for (int k = 0; k < OUT_LD; ++k) o[k] = 0.f;
+            for (int q = 0; q < ex.n_head_rows; ++q) {
+                float s = 0.f;
+                for (int t = 0; t < nct; ++t) s += hpart[((size_t)t * TCM + tid) * TC_HW + q];  // fixed order: deterministic
+                o[ex.head_col[q]] = s + __ldg(p.blob + ex.head_b[q]);
+            }
+            store_row(p, (size_t)grow, o, cenrow);
+        }
+        // the next tile's prologue ends with a cluster barrier: CTA 0 has finished reading hpart before any peer writes it
+        // again, and before its own producer refills the ring that hpart aliases (program order + fence.proxy.async)
     }
+    if (nt == 0) {
+        __syncthreads();  // every storing thread has fenced its peer stores (store_row)
+        if (tid == 0) gather_finish(p);  // fused all-gather: one arrival per cluster leader
+    }
+    tc_cluster_sync();  // no CTA exits while a peer may still address its shared memory
+    tmem_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// narrow head on an fp32 activation buffer: warp per 4 rows, lanes split K, shuffle reduction
-__global__ void tc_heads_kernel(const float* __restrict__ act, const float* __restrict__ W, const float* __restrict__ bias, int N, int K,
-                                int B, float* __restrict__ out_raw, int out_size, int out_col) {
-    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    const int row0 = warp * 4;
-    if (row0 >= B) return;
-    for (int o = 0; o < N; ++o) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = lane * 4; k < K; k += 128) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * K + k));
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (row0 + r < B) {
-                    const float4 a = *reinterpret_cast<const float4*>(act + (size_t)(row0 + r) * K + k);
-                    acc[r] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[r]))));
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            float s = acc[r];
-            for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
-            if (lane == 0 && row0 + r < B) out_raw[(size_t)(row0 + r) * out_size + out_col + o] = s + __ldg(bias + o);
-        }
-    }
 }
 
 }  // namespace mlb
@@ -264,125 +409,110 @@ __global__ void tc_heads_kernel(const float* __restrict__ act, const float* __re
 // ================================================================================================ host side
 using namespace mlb;
 
-struct mlb_tc {
-    int device, L, in_size, out_size, n_ops, max_rows_pad;
-    mlb_op ops[MLB_MAX_OPS];
-    float* blob_dev;
+struct mlb_tc_state {
     float* wplanes[MLB_MAX_OPS];
     int n_kb[MLB_MAX_OPS];
-    float *xplanes[2], *res_f32, *head_f32[2];
-    int* err_flag;
+    float* ws;
+    size_t slot_floats;
+    int max_clusters;
+    int nct;
 };
 
-extern thread_local std::string g_mlb_err;
-void mlb_count_launch();
-static int tc_fail(const std::string& m) {
-    g_mlb_err = m;
-    return -1;
-}
-#define TCC(call)                                                                                   \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess) return tc_fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
+bool mlb_tc_supported(int L) { return L >= TCN && L % TCN == 0 && L / TCN <= TC_MAX_CT; }
 
-extern "C" int mlb_tc_create(const mlb_model_desc* desc, const mlb_op* ops, const float* packed_host, size_t n_floats, int device,
-                             int max_rows, mlb_tc_handle* out) {
-    if (!desc || !ops || !packed_host || !out || max_rows < 1) return tc_fail("mlb_tc_create: bad argument");
-    if (desc->linear_size != 1024) return tc_fail("mlb_tc_create: the tensor-core path is written for linear_size == 1024");
-    if (desc->n_ops < 1 || desc->n_ops > MLB_MAX_OPS) return tc_fail("mlb_tc_create: n_ops out of range");
-    TCC(cudaSetDevice(device));
-    mlb_tc* t = new mlb_tc();
-    t->device = device, t->L = desc->linear_size, t->in_size = desc->input_size, t->out_size = desc->output_size, t->n_ops = desc->n_ops;
-    memcpy(t->ops, ops, sizeof(mlb_op) * desc->n_ops);
-    t->max_rows_pad = ((max_rows + TCM - 1) / TCM) * TCM;
-    TCC(cudaMalloc(&t->blob_dev, n_floats * sizeof(float)));
-    TCC(cudaMemcpy(t->blob_dev, packed_host, n_floats * sizeof(float), cudaMemcpyHostToDevice));
-    int n_gemm = 0;
-    for (int i = 0; i < desc->n_ops; ++i) {
+static cudaError_t tc_set_attr() {
+    cudaError_t e = cudaFuncSetAttribute(loco_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(loco_forward_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
+
+static void tc_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int clusters, int nct, cudaStream_t st) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->gridDim = dim3(clusters, nct);
+    cfg->blockDim = dim3(128);
+    cfg->dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg->stream = st;
+    at->id = cudaLaunchAttributeClusterDimension;
+    at->val.clusterDim.x = 1, at->val.clusterDim.y = nct, at->val.clusterDim.z = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = 1;
+}
+
+// pack the weight planes, size the workspace (one slot per co-resident cluster).  Returns nullptr + *err on failure.
+mlb_tc_state* mlb_tc_prepare(const float* blob_dev, const mlb_op* ops, int n_ops, int L, cudaStream_t st, cudaError_t* err) {
+    mlb_tc_state* t = new mlb_tc_state();
+    memset(t, 0, sizeof(*t));
+    t->nct = L / TCN;
+    *err = tc_set_attr();
+    if (*err != cudaSuccess) { delete t; return nullptr; }
+    int first = -1;
+    for (int i = 0; i < n_ops; ++i) {
         if (ops[i].type != MLB_OP_GEMM) continue;
-        if (++n_gemm > TC_MAX_LAYERS) return tc_fail("mlb_tc_create: too many layers");
+        if (first < 0) first = i;
         t->n_kb[i] = (ops[i].Kpad + TCKB - 1) / TCKB;
-        const size_t fl = (size_t)2 * t->n_kb[i] * TCKB * t->L;
-        TCC(cudaMalloc(&t->wplanes[i], fl * sizeof(float)));
-        tc_pack_weights_kernel<<<296, 256>>>(t->blob_dev + ops[i].w_off, t->wplanes[i], ops[i].Kpad, t->L, t->n_kb[i]);
+        const size_t fl = (size_t)2 * t->n_kb[i] * TCKB * L;
+        if ((*err = cudaMalloc(&t->wplanes[i], fl * sizeof(float))) != cudaSuccess) return nullptr;
+        tc_pack_weights_kernel<<<296, 256, 0, st>>>(blob_dev + ops[i].w_off, t->wplanes[i], ops[i].Kpad, L, t->n_kb[i]);
     }
-    const size_t act = (size_t)t->max_rows_pad * t->L;
-    for (int b = 0; b < 2; ++b) {
-        TCC(cudaMalloc(&t->xplanes[b], 2 * act * sizeof(float)));
-        TCC(cudaMemset(t->xplanes[b], 0, 2 * act * sizeof(float)));
-        TCC(cudaMalloc(&t->head_f32[b], act * sizeof(float)));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    tc_config(&cfg, &at, 64, t->nct, st);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, loco_forward_tc_kernel, &cfg) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 148 / t->nct / 2;
     }
-    TCC(cudaMalloc(&t->res_f32, act * sizeof(float)));
-    TCC(cudaMalloc(&t->err_flag, sizeof(int)));
-    TCC(cudaMemset(t->err_flag, 0, sizeof(int)));
-    TCC(cudaGetLastError());
-    TCC(cudaDeviceSynchronize());
-    *out = t;
-    return 0;
+    t->max_clusters = n;
+    const size_t plane = (size_t)TCM * TCKB;
+    t->slot_floats = (size_t)t->n_kb[first] * 2 * plane + 2 * (size_t)(L / TCKB) * 2 * plane + (size_t)TCM * L;
+    if ((*err = cudaMalloc(&t->ws, (size_t)n * t->slot_floats * sizeof(float))) != cudaSuccess) return nullptr;
+    if ((*err = cudaMemsetAsync(t->ws, 0, (size_t)n * t->slot_floats * sizeof(float), st)) != cudaSuccess) return nullptr;
+    *err = cudaGetLastError();
+    return t;
 }
 
-extern "C" void mlb_tc_destroy(mlb_tc_handle t) {
+cudaError_t mlb_tc_repack(mlb_tc_state* t, const float* blob_dev, const mlb_op* ops, int n_ops, int L, cudaStream_t st) {
+    for (int i = 0; i < n_ops; ++i)
+        if (ops[i].type == MLB_OP_GEMM)
+            tc_pack_weights_kernel<<<296, 256, 0, st>>>(blob_dev + ops[i].w_off, t->wplanes[i], ops[i].Kpad, L, t->n_kb[i]);
+    return cudaGetLastError();
+}
+
+void mlb_tc_free(mlb_tc_state* t) {
     if (!t) return;
-    cudaSetDevice(t->device);
-    cudaFree(t->blob_dev);
-    for (int i = 0; i < t->n_ops; ++i) cudaFree(t->wplanes[i]);
-    cudaFree(t->xplanes[0]), cudaFree(t->xplanes[1]), cudaFree(t->head_f32[0]), cudaFree(t->head_f32[1]);
-    cudaFree(t->res_f32), cudaFree(t->err_flag);
+    for (int i = 0; i < MLB_MAX_OPS; ++i) cudaFree(t->wplanes[i]);
+    cudaFree(t->ws);
     delete t;
 }
 
-// x_dev: pre-processed inputs [B, input_size] (MLB_IN_X); out_raw_dev: [B, output_size] raw network outputs
-extern "C" int mlb_tc_forward(mlb_tc_handle t, const float* x_dev, int B, float* out_raw_dev, void* stream) {
-    if (!t || !x_dev || !out_raw_dev || B < 1) return tc_fail("mlb_tc_forward: bad argument");
-    const int rows_pad = ((B + TCM - 1) / TCM) * TCM;
-    if (rows_pad > t->max_rows_pad) return tc_fail("mlb_tc_forward: more rows than mlb_tc_create reserved");
-    TCC(cudaSetDevice(t->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.L = t->L, p.rows_pad = rows_pad, p.err_flag = t->err_flag;
-    p.xplanes[0] = t->xplanes[0], p.xplanes[1] = t->xplanes[1], p.res_f32 = t->res_f32;
-    p.head_f32[0] = t->head_f32[0], p.head_f32[1] = t->head_f32[1];
-    int n_heads = 0, first = -1;
-    int head_of_layer[MLB_MAX_OPS];  // GEMM op index whose output each head op reads
-    for (int i = 0, last_gemm = -1; i < t->n_ops; ++i) {
-        head_of_layer[i] = -1;
-        if (t->ops[i].type == MLB_OP_GEMM) {
+int mlb_tc_clusters(const mlb_tc_state* t, int n_rows) {
+    const int tiles = (n_rows + TCM - 1) / TCM;
+    return tiles < t->max_clusters ? tiles : t->max_clusters;
+}
+
+cudaError_t mlb_tc_launch(const mlb_tc_state* t, const FwdParams& p, cudaStream_t st) {
+    TcExtra ex;
+    memset(&ex, 0, sizeof(ex));
+    for (int i = 0; i < MLB_MAX_OPS; ++i) ex.wplanes[i] = t->wplanes[i], ex.n_kb[i] = t->n_kb[i];
+    ex.ws = t->ws, ex.slot_floats = t->slot_floats;
+    ex.n_tiles = (p.n_rows + TCM - 1) / TCM;
+    int last_gemm = -1;
+    for (int i = 0; i < p.n_ops; ++i) {
+        const mlb_op& op = p.ops[i];
+        if (op.type == MLB_OP_GEMM) {
             last_gemm = i;
-            if (first < 0) first = i;
         } else {
-            if (last_gemm < 0) return tc_fail("mlb_tc_forward: a head before any layer");
-            head_of_layer[i] = last_gemm;
+            if (last_gemm < 0) return cudaErrorInvalidValue;
+            for (int o = 0; o < op.N; ++o) {
+                if (ex.n_head_rows >= TC_HW) return cudaErrorInvalidValue;
+                const int q = ex.n_head_rows++;
+                ex.head_src[q] = last_gemm, ex.head_col[q] = op.out_col + o;
+                ex.head_w[q] = op.w_off + (long long)o * op.K, ex.head_b[q] = op.shift_off + o;
+            }
         }
     }
-    int buf_of_gemm[MLB_MAX_OPS];
-    for (int i = 0; i < t->n_ops; ++i) buf_of_gemm[i] = -1;
-    for (int i = 0; i < t->n_ops; ++i)
-        if (head_of_layer[i] >= 0 && buf_of_gemm[head_of_layer[i]] < 0) {
-            if (n_heads >= 2) return tc_fail("mlb_tc_forward: more than two head inputs");
-            buf_of_gemm[head_of_layer[i]] = n_heads++;
-        }
-    for (int i = 0; i < t->n_ops; ++i) {
-        if (t->ops[i].type != MLB_OP_GEMM) continue;
-        TcLayer& ly = p.layer[p.n_layers++];
-        ly.wplanes = t->wplanes[i], ly.n_kb = t->n_kb[i], ly.flags = t->ops[i].flags, ly.head_buf = buf_of_gemm[i];
-        ly.scale = t->blob_dev + t->ops[i].scale_off, ly.shift = t->blob_dev + t->ops[i].shift_off;
-    }
-    tc_pack_input_kernel<<<296, 256, 0, st>>>(x_dev, t->xplanes[0], B, t->in_size, t->n_kb[first], rows_pad);
-    mlb_count_launch();
-    const size_t smem = (size_t)TCNST * TC_STAGE;
-    TCC(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_forward_kernel<<<dim3(rows_pad / TCM, 4), 128, smem, st>>>(p);
-    mlb_count_launch();
-    for (int i = 0; i < t->n_ops; ++i) {
-        if (t->ops[i].type != MLB_OP_HEAD) continue;
-        const mlb_op& op = t->ops[i];
-        const int warps = (B + 3) / 4;
-        tc_heads_kernel<<<(warps + 7) / 8, 256, 0, st>>>(t->head_f32[buf_of_gemm[head_of_layer[i]]], t->blob_dev + op.w_off,
-                                                        t->blob_dev + op.shift_off, op.N, op.K, B, out_raw_dev, t->out_size, op.out_col);
-        mlb_count_launch();
-    }
-    TCC(cudaGetLastError());
-    return 0;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at;
+    tc_config(&cfg, &at, mlb_tc_clusters(t, p.n_rows), t->nct, st);
+    return cudaLaunchKernelEx(&cfg, loco_forward_tc_kernel, p, ex);
 }

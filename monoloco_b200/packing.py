@@ -31,6 +31,17 @@ def num_stages(sd):
     return n
 
 
+def padded_width(linear_size):
+    """Hidden width the kernels run: the next multiple of 128 up to 1024 (FFMA kernels, and the tensor-core kernel when it
+    is also a multiple of 256), the next multiple of 256 up to 2048 beyond (tensor-core kernel only).  `--hidden_size`
+    is free in the reference (run.py:101,122; hyp_tuning.py:52 uses 2048)."""
+    if linear_size <= 1024:
+        return ((linear_size + 127) // 128) * 128
+    if linear_size <= 2048:
+        return ((linear_size + 255) // 256) * 256
+    raise ValueError("monoloco_b200: linear_size up to 2048 is supported (got %d)" % linear_size)
+
+
 class PackedModel:
     def __init__(self, desc, ops, blob, kind):
         self.desc, self.ops, self.blob, self.kind = desc, ops, blob, kind
@@ -39,7 +50,8 @@ class PackedModel:
 def pack_state_dict(sd, p_dropout=0.2):
     sd = {k: _np(v) for k, v in sd.items()}
     is_loco = 'w_fin.weight' in sd
-    L, in_size = sd['w1.weight'].shape
+    L_real, in_size = sd['w1.weight'].shape
+    L = padded_width(L_real)   # hidden units beyond L_real are zero columns / rows: they stay exactly 0 through every layer
     n_stage = num_stages(sd)
     chunks = []
     cursor = [0]
@@ -54,29 +66,35 @@ def pack_state_dict(sd, p_dropout=0.2):
     def affine(lin, bn):
         b = sd[lin + '.bias'].astype(np.float64)
         if bn is None:
-            return np.ones_like(b), b
-        s = sd[bn + '.weight'].astype(np.float64) / np.sqrt(sd[bn + '.running_var'].astype(np.float64) + BN_EPS)
-        return s, (b - sd[bn + '.running_mean'].astype(np.float64)) * s + sd[bn + '.bias'].astype(np.float64)
+            s, t = np.ones_like(b), b
+        else:
+            s = sd[bn + '.weight'].astype(np.float64) / np.sqrt(sd[bn + '.running_var'].astype(np.float64) + BN_EPS)
+            t = (b - sd[bn + '.running_mean'].astype(np.float64)) * s + sd[bn + '.bias'].astype(np.float64)
+        pad = L - s.size   # padded units: scale 1, shift 0 on an all-zero weight column -> 0 (and ReLU(0) = 0)
+        return np.concatenate([s, np.ones(pad)]), np.concatenate([t, np.zeros(pad)])
 
     ops = []
 
     def gemm(lin, bn, flags):
         w = sd[lin + '.weight']  # [N, K]
         n, k = w.shape
-        assert n == L
-        kpad = ((k + KC - 1) // KC) * KC
-        wt = np.zeros((kpad, n), dtype=np.float32)
-        wt[:k] = w.T
+        assert n == L_real
+        k_op = L if k == L_real and not (flags & L_.F_IN_XIN) else k   # hidden layers: K = padded width
+        kpad = ((k_op + KC - 1) // KC) * KC
+        wt = np.zeros((kpad, L), dtype=np.float32)
+        wt[:k, :n] = w.T
         s, t = affine(lin, bn)
-        ops.append(dict(type=L_.OP_GEMM, K=k, Kpad=kpad, N=n, flags=flags, out_col=0,
+        ops.append(dict(type=L_.OP_GEMM, K=k_op, Kpad=kpad, N=L, flags=flags, out_col=0,
                         w_off=put(wt), scale_off=put(s), shift_off=put(t)))
 
     def head(lin, out_col):
         w = sd[lin + '.weight']
         n, k = w.shape
-        assert k == L
-        ops.append(dict(type=L_.OP_HEAD, K=k, Kpad=k, N=n, flags=0, out_col=out_col,
-                        w_off=put(w), scale_off=0, shift_off=put(sd[lin + '.bias'])))
+        assert k == L_real
+        wp = np.zeros((n, L), dtype=np.float32)
+        wp[:, :k] = w
+        ops.append(dict(type=L_.OP_HEAD, K=L, Kpad=L, N=n, flags=0, out_col=out_col,
+                        w_off=put(wp), scale_off=0, shift_off=put(sd[lin + '.bias'])))
 
     gemm('w1', 'batch_norm1', L_.F_RELU | L_.F_DROPOUT | L_.F_IN_XIN | (L_.F_SAVE_RES if n_stage else 0))
     for i in range(n_stage):

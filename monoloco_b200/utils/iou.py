@@ -25,7 +25,9 @@ def get_iou_matches(boxes, boxes_gt, iou_min=0.3):
     """Greedy matching in decreasing confidence order; each ground truth used once (utils/iou.py:44-64)."""
     if not boxes or not boxes_gt:
         return []
-    order = list(np.argsort([b[4] for b in boxes]))[::-1]
+    # ties: the reference's default np.argsort is not a stable sort (its order of equal confidences depends on numpy's
+    # SIMD dispatch); here equal confidences are ordered by index, on the host and in the device kernel alike
+    order = list(np.argsort([b[4] for b in boxes], kind='stable'))[::-1]
     matches, used = [], []
     for idx in order:
         ious = [calculate_iou(boxes[idx], g) for g in boxes_gt]
@@ -39,6 +41,6 @@ def get_iou_matches(boxes, boxes_gt, iou_min=0.3):
 def reorder_matches(matches, boxes, mode='left_right'):
     """Sort matches by the detections' left edge (utils/iou.py:87-101)."""
     assert mode == 'left_right'
-    ordered = np.argsort([b[0] for b in boxes])
+    ordered = np.argsort([b[0] for b in boxes], kind='stable')
     left = [int(i) for i, _ in matches]
     return [matches[left.index(i)] for i in ordered if i in left]

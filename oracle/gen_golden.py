@@ -12,6 +12,7 @@ matplotlib is absent here; the reference imports pyplot at module import (net.py
 activity.py:10, losses.py:12), so it is stubbed with MagicMock before import.
 """
 import json
+import math
 import os
 import sys
 from unittest.mock import MagicMock
@@ -323,10 +324,37 @@ def ref_kitti_txt():
     print('ref_kitti_txt.json', len(out), 'files')
 
 
+def ref_activity():
+    """Outputs of the reference's activity helpers (monoloco/activity.py:17-67 social_interactions, probabilistic and
+    deterministic; :70-117 is_raising_hand) on a seeded crowd of 12 people standing 0.6-3 m apart and on the pifpaf
+    fixture's poses.  The seed is the first one whose flags contain both outcomes."""
+    from monoloco.activity import social_interactions, is_raising_hand
+    with open(os.path.join(OUT, 'pifpaf_002282.json')) as f:
+        _, keypoints = preprocess_pifpaf(json.load(f), im_size=(1238, 374))
+    raising = [is_raising_hand(k) for k in keypoints]
+    for seed in range(200):
+        rng = np.random.RandomState(seed)
+        n = 12
+        centers = np.stack([rng.uniform(-1.0, 2.5, n), rng.uniform(4.5, 9.5, n)], 1).tolist()
+        angles = rng.uniform(-math.pi, math.pi, n).tolist()
+        dds = [math.hypot(c[0], c[1]) for c in centers]
+        stds = rng.uniform(0.2, 1.0, n).tolist()
+        prob = [bool(social_interactions(i, centers, angles, dds, stds=stds)) for i in range(n)]
+        det = [bool(social_interactions(i, centers, angles, dds, stds=stds, n_samples=1)) for i in range(n)]
+        if 2 <= sum(prob) <= n - 2 and 1 <= sum(det) and prob != det:
+            break
+    out = {'seed': seed, 'centers': centers, 'angles': angles, 'dds': dds, 'stds': stds, 'prob': prob, 'det': det,
+           'raising': raising}
+    with open(os.path.join(OUT, 'ref_activity.json'), 'w') as f:
+        json.dump(out, f)
+    print('ref_activity.json seed', seed, 'prob', sum(prob), 'det', sum(det))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     steps = {'kat': kat_preprocess, 'forward': ref_forward, 'loco': ref_loco_forward, 'losses': ref_losses,
-             'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order, 'kitti': ref_kitti_txt}
+             'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order, 'kitti': ref_kitti_txt,
+             'activity': ref_activity}
     for name in (sys.argv[1:] or list(steps)):   # python oracle/gen_golden.py [step ...]
         steps[name]()
     print('done')

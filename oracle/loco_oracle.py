@@ -380,12 +380,20 @@ def close(a, b, rtol=1e-5, atol=1e-6, col_scale=True):
     return ok, worst
 
 
-def angle_close(a, b, rtol=1e-5, atol=1e-6):
-    """yaw comparison modulo 2pi (wrap at +-pi, camera.py:205-206)."""
+def angle_close(a, b, rtol=1e-5, atol=1e-6, radius=None, lin_tol=None):
+    """yaw comparison modulo 2pi (wrap at +-pi, camera.py:205-206).
+
+    An angle atan2(s, c) is only as well determined as its arguments: an error e on (s, c) moves it by up to e / hypot(s, c).
+    With `radius` (per-row hypot of the two arguments, reference values) and `lin_tol` (the tolerance the parity rule grants
+    those arguments), the tolerance of a row is max(rtol * pi + atol, lin_tol / radius) -- the angle subtended by the allowed
+    argument error.  Without them the rule is the flat rtol * pi + atol."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     diff = np.abs(np.where(np.isnan(a) | np.isnan(b), 0.0, a - b))
     diff = np.minimum(diff, np.abs(diff - 2 * math.pi))
-    tol = rtol * math.pi + atol
+    tol = np.full(diff.shape, rtol * math.pi + atol)
+    if radius is not None:
+        r = np.maximum(np.asarray(radius, dtype=np.float64).reshape(diff.shape), 1e-30)
+        tol = np.maximum(tol, float(lin_tol) / r)
     ok = bool((np.isnan(a) == np.isnan(b)).all() and (diff <= tol).all())
     return ok, float((diff / tol).max()) if diff.size else 0.0

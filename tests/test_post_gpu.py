@@ -161,7 +161,7 @@ def test_stereo_64x64_pairs_filter_vs_oracle():
     le, ri = synthetic.make_keypoints(64, seed=3, right=True)
     out = eng.forward(torch.from_numpy(le).cuda(), x_right=torch.from_numpy(ri).cuda(), kk=synthetic.KITTI_K,
                       kind=L_.IN_KPS_STEREO, want_xyzc=True)
-    pairs = O.preprocess_monstereo(le, ri, synthetic.KITTI_K)
+    pairs, _ = O.preprocess_monstereo(le, ri, synthetic.KITTI_K)
     assert pairs.shape == (4096, 68)
     ref_raw = O.loco_model_forward(sd, pairs)
     ok, worst = O.close(out['raw'].cpu().numpy(), ref_raw)

@@ -169,7 +169,9 @@ def test_train_dropout_rng_consistency():
     b = fused_train_forward(model, x, seed=11)
     c = fused_train_forward(model, x, seed=12)
     assert torch.equal(a, b) and not torch.equal(a, c)
-    a.sum().backward()
+    d = fused_train_forward(model, x, seed=11)   # backward belongs to the most recent train-mode forward (one workspace)
+    assert torch.equal(a, d)
+    d.sum().backward()
     assert torch.allclose(model.w_fin.bias.grad, torch.full((8,), 500.0, device='cuda'))
     assert float(model.w1.weight.grad.abs().sum()) > 0
 
