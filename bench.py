@@ -226,8 +226,8 @@ def extras(eng, sd, dev, flush, ffma_peak):
         for b in (1, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 65536):
             x = torch.from_numpy(synthetic.make_keypoints(b, seed=2)).to(dev)
             ms, _ = timed(lambda: eng.forward(x, kk=kk, kind=L_.IN_KPS), 20 if b <= 4096 else 3, dev)
-            lat[str(b)] = {"ms": ms, "tflops": fpd * b / ms / 1e9,
-                           "frac_fp32_peak": (fpd * b / ms / 1e9 / ffma_peak) if ffma_peak else None}
+            lat[str(b)] = {"ms": ms, "kernel": eng.last_kernel()[1], "tflops": fpd * b / ms / 1e9,
+                           "vs_fp32_ffma_peak": (fpd * b / ms / 1e9 / ffma_peak) if ffma_peak else None}
         out["forward_ms_by_batch"] = lat
         # ---- one image's worth of detections (<= 32 rows) is the weight-streaming regime (B <= ~19): the
         # whole-grid kernel against the HBM copy peak on the bytes it has to touch, L2 flushed (cold) and warm
@@ -248,8 +248,8 @@ def extras(eng, sd, dev, flush, ffma_peak):
         ms, _ = timed(lambda: meng.forward(x4k, kk=kk, kind=L_.IN_KPS), 10, dev, flush=flush)
         mf = packing.flops_per_detection(msd)
         out["monoloco_model_l1024_b4096"] = {"ms": ms, "detections_per_s": 4096 / (ms * 1e-3), "l2": "flushed",
-                                             "tflops": mf * 4096 / ms / 1e9,
-                                             "frac_fp32_peak": (mf * 4096 / ms / 1e9 / ffma_peak) if ffma_peak else None}
+                                             "kernel": meng.last_kernel()[1], "tflops": mf * 4096 / ms / 1e9,
+                                             "vs_fp32_ffma_peak": (mf * 4096 / ms / 1e9 / ffma_peak) if ffma_peak else None}
         meng.close()
         # ---- configs[2]: stereo 64 x 64 pairs + arg-max filter + xyz_from_distance
         seng = E.LocoEngine(synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2), device=dev)
@@ -443,6 +443,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
     eng.check_error()
+    eng.last_kernel_of_step = eng.last_kernel()
     per_step = torch.tensor([e0.elapsed_time(e1) for e0, e1 in ev], dtype=torch.float64, device=dev)
     total = per_step.sum().reshape(1)
     if world > 1:
@@ -530,6 +531,33 @@ def main():
         ffma_peak = engine.probe_ffma_tflops(local_rank)
         achieved_tf = flops / (ms_per_step * 1e-3) / 1e12
         tr = profile_json('forward_traffic.json')
+        kid, kname = eng.last_kernel_of_step
+        if kid == 3:
+            # tensor-core kernel: every fp32 product is three TF32 MMAs (hi.hi, lo.hi, hi.lo) -> executed tensor flops =
+            # 3 x algorithmic; TF32 dense peak = half the bf16 peak the driver measured (K = 8 vs 16 per instruction)
+            bf16_peak = float(pk.get('bf16_tflops', 2250.0 * 0.75))
+            tf32_peak = bf16_peak / 2.0
+            roof = {"bound": "tensor", "kernel": kname, "achieved": 3.0 * achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": 3.0 * achieved_tf / tf32_peak,
+                    "what": "executed TF32 tensor-core flops (3 MMAs per fp32 product: a_hi.w_hi, a_lo.w_hi, a_hi.w_lo) / kernel time",
+                    "peak_source": "TF32 dense = bf16 dense / 2; bf16 %.1f TFLOP/s %s" % (bf16_peak, 'measured (MEASURED_PEAKS.json, burst)' if 'bf16_tflops' in pk else 'fallback'),
+                    "algorithmic_flops": flops, "algorithmic_tflops": achieved_tf,
+                    "algorithmic_frac_of_tf32_peak": achieved_tf / tf32_peak,
+                    "algorithmic_vs_fp32_ffma_peak": achieved_tf / ffma_peak if ffma_peak else None,
+                    "fp32_ffma_peak": ffma_peak,
+                    "traffic": tr.get('traffic_bytes') if B == 4096 else None, "traffic_source": tr.get('source'),
+                    "algorithmic_bytes": alg_bytes}
+        else:
+            roof = {"bound": "fp32", "kernel": kname, "achieved": achieved_tf, "peak": ffma_peak, "unit": "TFLOP/s",
+                    "frac": achieved_tf / ffma_peak if ffma_peak else None,
+                    "peak_source": "measured in-run by mlb_probe_ffma (pure FFMA kernel; 148 SM x 128 lanes x 2 x clock)",
+                    "algorithmic_flops": flops,
+                    "traffic": tr.get('traffic_bytes') if B == 4096 else None, "traffic_source": tr.get('source'),
+                    "algorithmic_bytes": alg_bytes}
+        roof["hbm"] = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": achieved_gbs / hbm_peak, "peak_source": peak_src,
+                       "note": "not the binding bound at this batch (weights are read once, 34.9 MB per launch); see "
+                               "extras.small_batch_roofline for the <= 32-row regime where it is"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_step_stats": stats,
@@ -547,18 +575,9 @@ def main():
                     "ms_per_step": e2e_ms, "what": e2e_what},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            # binding bound first: at batch 4096 the path is FP32-FFMA bound; the HBM figure the
-            # metric string asks for is reported beside it (weights are read once, 34.9 MB per launch)
-            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": ffma_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / ffma_peak if ffma_peak else None,
-                         "peak_source": "measured in-run by mlb_probe_ffma (pure FFMA kernel; 148 SM x 128 lanes x 2 x clock)",
-                         "algorithmic_flops": flops,
-                         "traffic": tr.get('traffic_bytes') if B == 4096 else None, "traffic_source": tr.get('source'),
-                         "algorithmic_bytes": alg_bytes,
-                         "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": achieved_gbs / hbm_peak, "peak_source": peak_src,
-                                 "note": "not the binding bound at this batch; see extras.small_batch_roofline for the "
-                                         "<= 32-row regime where it is"}},
+            # binding bound first (the kernel that ran decides: tensor cores at this batch); the HBM figure the metric
+            # string asks for is nested beside it
+            "roofline": roof,
         }
         line.update(multi)
         if not args.no_extras and world == 1:

@@ -79,6 +79,14 @@ const char* mlb_last_error(void);
 int mlb_abi_version(void);
 /* number of SMs / resident CTAs the forward uses on this handle's device */
 int mlb_num_sms(mlb_handle h);
+/* which kernel the most recent mlb_forward on this handle launched (bench.py labels its roofline with it) */
+enum { MLB_KERNEL_TILE = 0,    /* loco_forward_kernel: one CTA per row tile, FFMA2                              */
+       MLB_KERNEL_CLUSTER = 1, /* loco_forward_cluster_kernel: 8-CTA cluster per 16 rows, FFMA2                 */
+       MLB_KERNEL_WIDE = 2,    /* loco_forward_wide_kernel: the whole grid on <= 32 rows                        */
+       MLB_KERNEL_TC = 3       /* loco_forward_tc_kernel: tcgen05 kind::tf32, 3 MMAs per fp32 product           */ };
+int mlb_last_kernel(mlb_handle h);
+/* co-resident clusters of the tensor-core kernel on this device (= its persistent grid size), 0 if unavailable */
+int mlb_tc_resident_clusters(mlb_handle h);
 /* device error word of this handle (mapped host memory; read it after a stream synchronisation): 0 = none,
  * 1 = a TMA/mbarrier wait timed out, 3 = grid-barrier time-out (whole-grid kernel), 4 = fused all-gather: a peer
  * rank did not signal its epoch within 20 s. */

@@ -18,8 +18,10 @@ DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
 IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH, FWD_FORCE_WIDE = 1, 2, 4, 8, 16, 32, 64
 FWD_FORCE_TC = 128
+KERNEL_NAMES = {0: 'loco_forward_kernel (FFMA2 row tiles)', 1: 'loco_forward_cluster_kernel (FFMA2, 8-CTA clusters)',
+                2: 'loco_forward_wide_kernel (FFMA, whole grid)', 3: 'loco_forward_tc_kernel (tcgen05 3xTF32)'}
 
-EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error',
+EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error', 'mlb_last_kernel', 'mlb_tc_resident_clusters',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_post_process', 'mlb_kitti_rows', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
            'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
            'mlb_adam_clip_step',
@@ -102,6 +104,8 @@ def lib():
     l.mlb_destroy.restype = None
     l.mlb_num_sms.argtypes = [C.c_void_p]
     l.mlb_device_error.argtypes = [C.c_void_p]
+    l.mlb_last_kernel.argtypes = [C.c_void_p]
+    l.mlb_tc_resident_clusters.argtypes = [C.c_void_p]
     l.mlb_forward.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_forward_host.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_preprocess.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p, C.c_void_p]

@@ -553,6 +553,8 @@ cudaError_t mlb_tc_repack(mlb_tc_state* t, const float* blob_dev, const mlb_op* 
 void mlb_tc_free(mlb_tc_state* t);
 int mlb_tc_clusters(const mlb_tc_state* t, int n_rows);
 cudaError_t mlb_tc_launch(const mlb_tc_state* t, const FwdParams& p, cudaStream_t st);
+cudaError_t mlb_tc_set_marks(unsigned long long* ptr);
+int mlb_tc_max_clusters(const mlb_tc_state* t);
 // forward_wide.cu
 size_t mlb_wide_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab_off);
 cudaError_t mlb_wide_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, const long long* slab_off, cudaStream_t st);
@@ -581,6 +583,7 @@ struct mlb_model {
     float* res_scratch;
     size_t res_floats;
     mlb_tc_state* tc;              // tensor-core kernel state (weight planes, cluster workspace), or null
+    int last_kernel;               // MLB_KERNEL_* of the most recent mlb_forward launch
     bool ffma_ok;                  // the FFMA kernels fit this width (L <= 1024)
     int tc_min_rows;               // batches of at least this many rows go to the tensor-core kernel
     unsigned* gather_done;         // monotonic count of CTAs that finished their peer stores (fused all-gather)
@@ -625,6 +628,7 @@ extern "C" int mlb_debug_fwd_marks(void* dev_buf) {
     unsigned long long* ptr = reinterpret_cast<unsigned long long*>(dev_buf);
     cudaError_t e = cudaMemcpyToSymbol(mlb::g_fwd_marks, &ptr, sizeof(ptr));
     if (e == cudaSuccess) e = mlb_wide_set_marks(ptr);
+    if (e == cudaSuccess) e = mlb_tc_set_marks(ptr);
     if (e != cudaSuccess) {
         g_mlb_err = std::string("mlb_debug_fwd_marks: ") + cudaGetErrorString(e);
         return -1;
@@ -632,6 +636,8 @@ extern "C" int mlb_debug_fwd_marks(void* dev_buf) {
     return 0;
 }
 extern "C" int mlb_num_sms(mlb_handle h) { return h ? h->n_sms : 0; }
+extern "C" int mlb_last_kernel(mlb_handle h) { return h ? h->last_kernel : -1; }
+extern "C" int mlb_tc_resident_clusters(mlb_handle h) { return (h && h->tc) ? mlb_tc_max_clusters(h->tc) : 0; }
 extern "C" int mlb_device_error(mlb_handle h) { return h ? *reinterpret_cast<volatile int*>(h->err_flag_host) : -1; }
 
 static size_t fwd_smem_bytes(int L) {
@@ -690,9 +696,6 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
             cudaGetLastError();  // the FFMA kernels cover this width: carry on without the tensor-core path
         }
         CU(cudaDeviceSynchronize());
-        // measured: one wave of 128-row tiles takes ~0.47 ms whatever the batch; the FFMA cluster / tile
-        // kernels pass that mark between 384 and 512 rows
-        m->tc_min_rows = getenv("MLB_TC_MIN_ROWS") ? atoi(getenv("MLB_TC_MIN_ROWS")) : 448;
     }
     if (L == 1024) {
         size_t gemm_floats = 0;
@@ -703,6 +706,14 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
         CU(cudaDeviceSynchronize());
         m->small_conc = mlb_small_max_clusters(L);
         if (m->small_conc < 1) m->small_conc = 8;
+    }
+    if (m->tc != nullptr) {
+        // When the tensor-core kernel takes over (measured): a wave of 128-row tiles takes ~0.32 ms whatever
+        // the batch.  One wave of 8-CTA FFMA clusters (16 rows each, `small_conc` co-resident) takes 0.18 ms, two take
+        // 0.36 ms: the cluster kernel keeps the batches that fit ONE wave.  Without the cluster kernel (L != 1024) a
+        // row-tile wave costs >= 0.9 ms, so everything beyond the whole-grid kernel's 64 rows goes to the tensor cores.
+        m->tc_min_rows = m->slab_dev != nullptr ? m->small_conc * 16 + 1 : 65;
+        if (getenv("MLB_TC_MIN_ROWS")) m->tc_min_rows = atoi(getenv("MLB_TC_MIN_ROWS"));
     }
     if (ffma_ok && mlb_wide_supported(L, m->n_sms)) {
         const size_t wf = mlb_wide_slab_floats(m->ops, desc->n_ops, L, m->wslab_off);
@@ -878,6 +889,7 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
         cudaError_t et = mlb_tc_launch(h->tc, p, st);
         if (et != cudaSuccess) return fail(std::string("loco_forward_tc_kernel launch: ") + cudaGetErrorString(et));
         g_launches++;
+        h->last_kernel = MLB_KERNEL_TC;
         return 0;
     }
 
@@ -910,7 +922,10 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
             }
             g_launches++;
         }
-        if (wide_ok) return 0;
+        if (wide_ok) {
+            h->last_kernel = MLB_KERNEL_WIDE;
+            return 0;
+        }
         h->wide_disabled = true;
         p.row_base = 0;
     }
@@ -930,6 +945,7 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
             cudaError_t es = mlb_small_launch(p, h->slab_dev, h->slab_off, n_clusters < conc ? n_clusters : conc, st);
             if (es != cudaSuccess) return fail(std::string("loco_forward_cluster_kernel launch: ") + cudaGetErrorString(es));
             g_launches++;
+            h->last_kernel = MLB_KERNEL_CLUSTER;
             return 0;
         }
     } else if (a->flags & MLB_FWD_FORCE_CLUSTER) {
@@ -963,6 +979,7 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     }
     if (e != cudaSuccess) return fail(std::string("loco_forward_kernel launch: ") + cudaGetErrorString(e));
     g_launches++;
+    h->last_kernel = MLB_KERNEL_TILE;
     return 0;
 }
 

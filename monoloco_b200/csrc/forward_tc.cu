@@ -35,18 +35,23 @@
 
 namespace mlb {
 
-constexpr int TCM = 128, TCN = 256, TCKB = 16, TCNST = 4;
-constexpr uint32_t TC_A_PLANE = TCM * TCKB * 4, TC_W_PLANE = TCN * TCKB * 4;  // bytes
-constexpr uint32_t TC_STAGE = 2 * TC_A_PLANE + 2 * TC_W_PLANE;                 // 48 KB
+constexpr int TCM = 128, TCN = 256, TCH = 128, TCKB = 16, TCNST = 4;   // row tile, columns per CTA, columns per epilogue half, k block, ring
+constexpr uint32_t TC_A_PLANE = TCM * TCKB * 4;   // bytes of one X plane block (128 rows x 16 k)
+constexpr uint32_t TC_W_PLANE = TCN * TCKB * 4;   // bytes of one W plane block (256 output columns x 16 k)
+constexpr uint32_t TC_STAGE = 2 * TC_A_PLANE + 2 * TC_W_PLANE;   // 48 KB: X hi|lo + W hi|lo
 constexpr uint32_t TC_LBO_A = TCM * 16, TC_LBO_W = TCN * 16, TC_SBO = 128;
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
 constexpr int TC_MAX_CT = 8;       // column tiles = CTAs per cluster (L <= 2048)
 constexpr int TC_HW = 16;          // head output columns in total (output_size <= 16)
-constexpr size_t TC_RING_BYTES = (size_t)TCNST * TC_STAGE;
-constexpr size_t TC_SMEM_BYTES = TC_RING_BYTES + (size_t)TC_HW * TCN * sizeof(float);  // ring + this CTA's head-weight slice
+constexpr int TC_EPI = 256;        // epilogue threads: (row, column half) -- warps w and w + 4 share a TMEM lane quarter
+constexpr int TC_THREADS = 256;    // 8 warps: all epilogue; thread 0 also issues the MMAs, thread 128 also drives the TMA ring
+constexpr size_t TC_RING_BYTES = (size_t)TCNST * TC_STAGE;                      // 192 KB
+constexpr size_t TC_SST_BYTES = 2 * TCN * sizeof(float);                        // folded-BN scale | shift of the layer
+constexpr size_t TC_HW_BYTES = (size_t)TC_HW * TCN * sizeof(float);             // head weights of the layer
+constexpr size_t TC_SMEM_BYTES = TC_RING_BYTES + TC_SST_BYTES + TC_HW_BYTES;    // 210 KB
 
 struct TcExtra {
-    const float* wplanes[MLB_MAX_OPS];  // per GEMM op: [L/256][n_kb][hi|lo][256 x 16]
+    const float* wplanes[MLB_MAX_OPS];  // per GEMM op: [L/256 column tiles][n_kb][hi|lo][256 x 16]
     int n_kb[MLB_MAX_OPS];              // K blocks of 16 (K zero-padded)
     float* ws;                          // workspace, one slot per cluster
     unsigned long long slot_floats;
@@ -90,31 +95,27 @@ __device__ __forceinline__ void tc_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 epilogue warps
 __device__ __forceinline__ uint32_t tc_cluster_id() {  // clusters are laid out along x: one cluster per blockIdx.x
     return blockIdx.x;
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {  // 32 consecutive TMEM columns of this thread's lane
-    uint32_t r[32];
+// 16 consecutive TMEM columns of this thread's lane, asynchronous: complete after tc_ld_wait()
+__device__ __forceinline__ void tc_ld16_async(uint32_t taddr, uint32_t* r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // float offset of element (row r, k) inside one [tile_rows x 16] plane
-__device__ __forceinline__ size_t tc_plane_off(int r, int k_in_block, int tile_rows) {
+__device__ __forceinline__ size_t tc_plane_off(int r, int k_in_block, int tile_rows = TCM) {
     return (size_t)(k_in_block >> 2) * tile_rows * 4 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4 + (k_in_block & 3);
 }
 
-// W^T [Kpad][L] (the packed blob's layout) -> W planes with K padded to n_kb * 16
+// W^T [Kpad][L] (the packed blob's layout) -> W planes [L/256][n_kb][hi|lo][256 x 16] with K padded to n_kb * 16
 __global__ void tc_pack_weights_kernel(const float* __restrict__ wt, float* __restrict__ planes, int Kpad, int L, int n_kb) {
     const int K = n_kb * TCKB;
     const size_t plane = (size_t)TCN * TCKB;
@@ -129,31 +130,154 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wt, float* __re
     }
 }
 
-__global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ TcExtra ex) {
+// profiling aid (mlb_debug_fwd_marks): CTA (0,0) stamps %globaltimer per layer of its first tile: thread 0 at [8g+0] layer start,
+// [8g+3] accumulators complete, [8g+4] epilogue done, [8g+5] cluster barrier passed; MMA lane at [8g+1] first stage landed,
+// [8g+2] all MMAs issued; producer lane at [8g+6] all stages issued
+__device__ unsigned long long* g_tc_marks = nullptr;
+__device__ __forceinline__ void tmark(unsigned long long* marks, int slot) {
+    if (marks != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        marks[slot] = t;
+    }
+}
+
+struct TcEpi {            // what one epilogue pass over a 128-column half needs
+    uint32_t tmem_main;   // TMEM address of this thread's lane, main accumulator of the half (cross terms at + 256)
+    const float* sst;     // shared: scale[256] | shift[256] of the CTA's columns
+    const float* hw;      // shared: [NQ][256] weights of the head rows this layer feeds (zero rows beyond the real ones)
+    float* nxt;           // next layer's X planes (cluster slot)
+    float* res;           // fp32 residual [L/4][128][4] (cluster slot)
+    int col0;             // first global column of the half
+    int ccol0;            // first CTA-local column of the half (0 or 128)
+    int tid, grow, site;
+    bool live, relu, add_res, save_res, drop;
+    const uint8_t* drop_mask;
+    int n_rows, L;
+    uint32_t rm, thr;
+    float inv_keep;
+};
+
+// MC-dropout of four consecutive columns (rare path, kept out of line: the epilogue loops must stay small enough for the
+// instruction cache -- fully unrolled they were 140 KB per instantiation and every first use cost ~15 us of code fetch)
+__device__ __noinline__ float4 tc_dropout4(float4 v, const uint8_t* mask_row, uint32_t rm, uint32_t thr, float inv_keep, int gc, int site,
+                                           int live) {
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (mask_row != nullptr) {
+        if (live) {
+            const uint32_t mk = *reinterpret_cast<const uint32_t*>(mask_row + gc);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = ((mk >> (8 * t)) & 0xFFu) ? o[t] * inv_keep : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) o[t] = drop_keep(rm, drop_col_hash((uint32_t)(gc + t), (uint32_t)site), thr) ? o[t] * inv_keep : 0.f;
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
+constexpr int TC_CW = 16;   // accumulator columns per epilogue chunk (one tcgen05.ld x16 per accumulator)
+
+// One 16-column chunk of this thread's row: BN affine / ReLU / dropout / residual, head partial sums, hi / lo planes out.
+template <int NQ, int OFF, bool ADD>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, int ch, const uint32_t* mb, const uint32_t* cb, const float4* rr,
+                                                  float* hacc) {
+    constexpr size_t plane = (size_t)TCM * TCKB;
+#pragma unroll
+    for (int j4 = 0; j4 < TC_CW / 4; ++j4) {
+        const int lc = e.ccol0 + TC_CW * ch + 4 * j4;   // CTA-local column
+        const int gc = e.col0 + TC_CW * ch + 4 * j4;    // global column = k index of the next layer
+        const float4 sc = *reinterpret_cast<const float4*>(e.sst + lc);
+        const float4 sh = *reinterpret_cast<const float4*>(e.sst + TCN + lc);
+        float v[4];
+        v[0] = fmaf(__uint_as_float(mb[4 * j4 + 0]) + __uint_as_float(cb[4 * j4 + 0]), sc.x, sh.x);
+        v[1] = fmaf(__uint_as_float(mb[4 * j4 + 1]) + __uint_as_float(cb[4 * j4 + 1]), sc.y, sh.y);
+        v[2] = fmaf(__uint_as_float(mb[4 * j4 + 2]) + __uint_as_float(cb[4 * j4 + 2]), sc.z, sh.z);
+        v[3] = fmaf(__uint_as_float(mb[4 * j4 + 3]) + __uint_as_float(cb[4 * j4 + 3]), sc.w, sh.w);
+        if (e.relu) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[t] = fmaxf(v[t], 0.f);
+        }
+        if (e.drop) {
+            const uint8_t* mrow = e.drop_mask ? e.drop_mask + ((size_t)e.site * e.n_rows + e.grow) * e.L : nullptr;
+            const float4 d = tc_dropout4(make_float4(v[0], v[1], v[2], v[3]), mrow, e.rm, e.thr, e.inv_keep, gc, e.site, (int)e.live);
+            v[0] = d.x, v[1] = d.y, v[2] = d.z, v[3] = d.w;
+        }
+        float* rq = e.res + ((size_t)(gc >> 2) * TCM + e.tid) * 4;   // a warp touches 512 contiguous bytes
+        if (ADD) {
+            const float4 r = rr[j4];
+            v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
+        }
+        if (e.save_res) *reinterpret_cast<float4*>(rq) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {   // narrow heads on this layer's output: partial dot products over my columns
+            const float4 w = *reinterpret_cast<const float4*>(e.hw + q * TCN + lc);
+            hacc[OFF + q] = fmaf(v[3], w.w, fmaf(v[2], w.z, fmaf(v[1], w.y, fmaf(v[0], w.x, hacc[OFF + q]))));
+        }
+        float* blk = e.nxt + (size_t)(gc / TCKB) * 2 * plane;
+        const float4 h = make_float4(tc_tf32(v[0]), tc_tf32(v[1]), tc_tf32(v[2]), tc_tf32(v[3]));
+        const float4 l = make_float4(tc_tf32(v[0] - h.x), tc_tf32(v[1] - h.y), tc_tf32(v[2] - h.z), tc_tf32(v[3] - h.w));
+        const size_t off = tc_plane_off(e.tid, gc % TCKB);
+        *reinterpret_cast<float4*>(blk + off) = h;
+        *reinterpret_cast<float4*>(blk + plane + off) = l;
+    }
+}
+
+// The 128 accumulator columns of this thread's row, two chunks per (rolled) loop trip; TMEM loads and residual loads are
+// double-buffered: the next chunk is in flight while the current one is processed.
+template <int NQ, int OFF, bool ADD>
+__device__ __forceinline__ void tc_epilogue_half(const TcEpi& e, float* hacc) {
+    constexpr int NCH = TCH / TC_CW, RW = ADD ? TC_CW / 4 : 1;
+    uint32_t mb0[TC_CW], cb0[TC_CW], mb1[TC_CW], cb1[TC_CW];
+    float4 rr0[RW], rr1[RW];
+    const float* res_row = e.res + ((size_t)(e.col0 >> 2) * TCM + e.tid) * 4;   // + 512 floats per 4 columns
+    auto fetch = [&](int ch, uint32_t* mb, uint32_t* cb, float4* rr) {
+        tc_ld16_async(e.tmem_main + (uint32_t)(TC_CW * ch), mb);
+        tc_ld16_async(e.tmem_main + 256u + (uint32_t)(TC_CW * ch), cb);
+        if (ADD) {
+#pragma unroll
+            for (int j4 = 0; j4 < TC_CW / 4; ++j4)
+                rr[j4] = *reinterpret_cast<const float4*>(res_row + (size_t)(ch * (TC_CW / 4) + j4) * TCM * 4);
+        }
+    };
+    fetch(0, mb0, cb0, rr0);
+    tc_ld_wait();
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ch += 2) {
+        fetch(ch + 1, mb1, cb1, rr1);
+        tc_epilogue_chunk<NQ, OFF, ADD>(e, ch, mb0, cb0, rr0, hacc);
+        tc_ld_wait();
+        if (ch + 2 < NCH) fetch(ch + 2, mb0, cb0, rr0);
+        tc_epilogue_chunk<NQ, OFF, ADD>(e, ch + 1, mb1, cb1, rr1, hacc);
+        tc_ld_wait();
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __grid_constant__ FwdParams p,
+                                                                        const __grid_constant__ TcExtra ex) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[TCNST], empty[TCNST], done;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = blockIdx.y, nct = gridDim.y, L = p.L;
-    float* hw = reinterpret_cast<float*>(smem_raw + TC_RING_BYTES);  // [TC_HW][256] head weights of this CTA's columns
-    float* hpart = reinterpret_cast<float*>(smem_raw);               // [nct][128][TC_HW] on CTA 0; aliases the idle ring
+    const bool epi_thread = true, prod_lane = tid == 128, mma_lane = tid == 0;
+    const int half = (tid >> 7) & 1;   // epilogue threads: which 128 columns of the CTA's 256
+    float* sst = reinterpret_cast<float*>(smem_raw + TC_RING_BYTES);                 // [2][256]
+    float* hw = reinterpret_cast<float*>(smem_raw + TC_RING_BYTES + TC_SST_BYTES);   // [TC_HW][256]
+    float* hpart = reinterpret_cast<float*>(smem_raw);                               // [2 nct][128][TC_HW] on CTA 0; aliases the idle ring
 
     if (tid == 0) {
         for (int s = 0; s < TCNST; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
         mbar_init(&done, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < TC_HW * TCN; i += 128) {
-        const int q = i / TCN, c = i % TCN;
-        hw[i] = q < ex.n_head_rows ? __ldg(p.blob + ex.head_w[q] + nt * TCN + c) : 0.f;
-    }
-    if (warp == 0) tmem_alloc(&tmem_slot, 512);  // [0,256) main accumulator, [256,512) cross terms
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);  // main accumulator [0,256), cross terms [256,512)
     tmem_fence_before();
     __syncthreads();
     tmem_fence_after();
     tc_cluster_sync();  // every CTA of the cluster is resident before any remote shared-memory store can be issued
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
     // this cluster's workspace slot
     int first_gemm = 0;
@@ -163,24 +287,35 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
     float* slot = ex.ws + (size_t)tc_cluster_id() * ex.slot_floats;
     float* xin = slot;                                   // [n_kb0][hi|lo][128 x 16]
     float* xpl[2] = {xin + (size_t)n_kb0 * 2 * plane, xin + (size_t)n_kb0 * 2 * plane + (size_t)(L / TCKB) * 2 * plane};
-    float* res = xpl[1] + (size_t)(L / TCKB) * 2 * plane;  // [128][L] fp32
+    float* res = xpl[1] + (size_t)(L / TCKB) * 2 * plane;  // [L/4][128][4] fp32
 
     const float zm = p.z_met;
     const float k0 = p.kinv[0], k1 = p.kinv[1], k2 = p.kinv[2], k3 = p.kinv[3], k4 = p.kinv[4], k5 = p.kinv[5];
     const bool mc_drop = (p.flags & MLB_FWD_DROPOUT) != 0;
-    const float inv_keep = 1.0f / (1.0f - p.p_drop);
-    const uint32_t seed_mix = drop_seed_mix(p.drop_seed), thr = drop_threshold(p.p_drop);
+    // head rows are grouped by the layer that feeds them (at most two groups: w_aux | w_fin, or MonolocoModel.w2); group g
+    // accumulates into hacc[off_g .. off_g + nq_g), nq_g = its row count rounded up to 4 (zero weights beyond the real rows)
+    int grp_src[2] = {-1, -1}, grp_q0[2] = {0, 0}, grp_n[2] = {0, 0};
+    for (int q = 0; q < ex.n_head_rows; ++q) {
+        const int g = (grp_src[0] < 0 || grp_src[0] == ex.head_src[q]) ? 0 : 1;
+        if (grp_n[g] == 0) grp_src[g] = ex.head_src[q], grp_q0[g] = q;
+        grp_n[g]++;
+    }
+    const int grp_nq[2] = {(grp_n[0] + 3) & ~3, (grp_n[1] + 3) & ~3};
+    const int grp_off[2] = {0, grp_nq[0]};
 
+    unsigned long long* marks = (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 128)) ? g_tc_marks : nullptr;
     unsigned it_p = 0, it_m = 0;  // stages issued / consumed so far (producer lane, MMA lane)
     unsigned n_done = 0;          // layers finished by this CTA (parity of `done`)
     for (int rb = (int)tc_cluster_id(); rb < ex.n_tiles; rb += (int)gridDim.x) {
-        const int grow = rb * TCM + tid;  // this thread's detection
-        const bool live = grow < p.n_rows;
+        const int row = tid & 127;            // epilogue threads: my row of the tile
+        const int grow = rb * TCM + row;      // my detection
+        const bool live = epi_thread && grow < p.n_rows;
+        const bool row_owner = epi_thread && half == 0;   // one thread per row does the prologue / the final store
         float cenrow[4] = {0.f, 0.f, 0.f, 0.f};
 
         // ------------------------------------------------------------ prologue: network input of my row -> hi / lo planes
         // every CTA of the cluster evaluates its row (cheap); CTA nt writes k blocks nt, nt + nct, ...
-        {
+        if (row_owner) {
             float xr[KIN_MAX + 8];
 #pragma unroll
             for (int k = 0; k < KIN_MAX + 8; ++k) xr[k] = 0.f;
@@ -236,7 +371,7 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
                         const float4 v = make_float4(xr[kb * 16 + 4 * q], xr[kb * 16 + 4 * q + 1], xr[kb * 16 + 4 * q + 2], xr[kb * 16 + 4 * q + 3]);
                         const float4 h = make_float4(tc_tf32(v.x), tc_tf32(v.y), tc_tf32(v.z), tc_tf32(v.w));
                         const float4 l = make_float4(tc_tf32(v.x - h.x), tc_tf32(v.y - h.y), tc_tf32(v.z - h.z), tc_tf32(v.w - h.w));
-                        const size_t off = tc_plane_off(tid, 4 * q, TCM);
+                        const size_t off = tc_plane_off(row, 4 * q);
                         *reinterpret_cast<float4*>(blk + off) = h;
                         *reinterpret_cast<float4*>(blk + plane + off) = l;
                     }
@@ -255,7 +390,12 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
             if (op.type != MLB_OP_GEMM) continue;
             const int n_kb = ex.n_kb[oi];
             const float* xsrc_f = gi == 0 ? xin : xpl[par];
-            if (warp == 1 && lane == 0) {
+            unsigned long long* mk = (rb == 0 && gi < 15) ? marks : nullptr;
+            if (tid == 0) tmark(mk, 8 * gi + 0);
+            const int hg = grp_src[0] == oi ? 0 : (grp_src[1] == oi ? 1 : -1);   // head group fed by this layer
+            const bool head_layer = hg >= 0;
+
+            if (prod_lane) {
                 // ---- producer: this row tile's X planes and this column tile's W planes, 48 KB per stage
                 asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy stores (planes, hpart) -> async-proxy TMA
                 const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(xsrc_f);
@@ -268,13 +408,15 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
                     tma_bulk_g2s(st, xsrc + (size_t)kb * 2 * TC_A_PLANE, 2 * TC_A_PLANE, &full[s]);
                     tma_bulk_g2s(st + 2 * TC_A_PLANE, wsrc + (size_t)kb * 2 * TC_W_PLANE, 2 * TC_W_PLANE, &full[s]);
                 }
-            } else if (warp == 0 && lane == 0) {
-                // ---- MMA issuer
+                tmark(mk, 8 * gi + 6);
+            } else if (mma_lane) {
+                // ---- MMA issuer: 2 k-steps x 3 MMAs (M 128, N 256, K 8) per stage
                 tmem_fence_after();
                 uint32_t main_acc = 0, cross_acc = 0;
                 for (int kb = 0; kb < n_kb; ++kb, ++it_m) {
                     const unsigned s = it_m % TCNST;
                     mbar_wait(&full[s], (it_m / TCNST) & 1, p.err_flag);
+                    if (kb == 0) tmark(mk, 8 * gi + 1);
                     tmem_fence_after();
                     const uint32_t a_hi = smem_u32(smem_raw + (size_t)s * TC_STAGE), a_lo = a_hi + TC_A_PLANE;
                     const uint32_t w_hi = a_hi + 2 * TC_A_PLANE, w_lo = w_hi + TC_W_PLANE;
@@ -282,95 +424,85 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
                     for (int j = 0; j < TCKB / 8; ++j) {
                         const uint64_t ah = tc_desc(a_hi + 2 * j * TC_LBO_A, TC_LBO_A), al = tc_desc(a_lo + 2 * j * TC_LBO_A, TC_LBO_A);
                         const uint64_t wh = tc_desc(w_hi + 2 * j * TC_LBO_W, TC_LBO_W), wl = tc_desc(w_lo + 2 * j * TC_LBO_W, TC_LBO_W);
-                        tc_mma(tmem + TCN, al, wh, cross_acc), cross_acc = 1;
-                        tc_mma(tmem + TCN, ah, wl, 1u);
+                        tc_mma(tmem + 256u, al, wh, cross_acc), cross_acc = 1;
+                        tc_mma(tmem + 256u, ah, wl, 1u);
                         tc_mma(tmem, ah, wh, main_acc), main_acc = 1;
                     }
                     tc_commit(&empty[s]);
                 }
                 tc_commit(&done);
-            }
-            __syncwarp();
-            mbar_wait_backoff(&done, (uint32_t)(n_done & 1), p.err_flag);
-            ++n_done;
-            tmem_fence_after();
-
-            // ---- epilogue: thread = row; columns [256 nt, 256 nt + 256) in steps of 32
-            float* nxt = xpl[gi == 0 ? 0 : (par ^ 1)];
-            const bool relu = (op.flags & MLB_F_RELU) != 0, add_res = (op.flags & MLB_F_ADD_RES) != 0,
-                       save_res = (op.flags & MLB_F_SAVE_RES) != 0;
-            const bool drop = mc_drop && (op.flags & MLB_F_DROPOUT) != 0;
-            const uint32_t rm = drop_row_mix(seed_mix, (uint32_t)grow);
-            int q_lo = TC_HW, q_hi = 0;  // head rows fed by this layer's output
-            for (int q = 0; q < ex.n_head_rows; ++q)
-                if (ex.head_src[q] == oi) q_lo = min(q_lo, q), q_hi = max(q_hi, q + 1);
-            float* res_row = res + (size_t)tid * L + nt * TCN;
-            for (int c0 = 0; c0 < TCN; c0 += 32) {
-                float m[32], c[32];
-                tc_ld32(lane_base + (uint32_t)c0, m);
-                tc_ld32(lane_base + (uint32_t)(TCN + c0), c);
-                const int col = nt * TCN + c0;
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.blob + op.scale_off + col + 4 * j4));
-                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.blob + op.shift_off + col + 4 * j4));
-                    float v[4];
-                    v[0] = fmaf(m[4 * j4 + 0] + c[4 * j4 + 0], sc.x, sh.x);
-                    v[1] = fmaf(m[4 * j4 + 1] + c[4 * j4 + 1], sc.y, sh.y);
-                    v[2] = fmaf(m[4 * j4 + 2] + c[4 * j4 + 2], sc.z, sh.z);
-                    v[3] = fmaf(m[4 * j4 + 3] + c[4 * j4 + 3], sc.w, sh.w);
-                    if (relu) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                tmark(mk, 8 * gi + 2);
+            } else if (warp != 0 && warp != 4) {
+                // ---- the other six warps, while the MMAs run: this layer's epilogue constants -> shared memory
+                const int st = tid < 128 ? tid - 32 : tid - 64;   // 0 .. 191
+                for (int i = st; i < 2 * TCN; i += 192)
+                    sst[i] = __ldg(p.blob + (i < TCN ? op.scale_off : op.shift_off) + nt * TCN + (i & (TCN - 1)));
+                if (head_layer) {
+                    for (int i = st; i < grp_nq[hg] * TCN; i += 192) {
+                        const int r = i / TCN, c = i % TCN;
+                        hw[i] = r < grp_n[hg] ? __ldg(p.blob + ex.head_w[grp_q0[hg] + r] + nt * TCN + c) : 0.f;
                     }
-                    if (drop) {
-                        if (p.drop_mask != nullptr) {
-                            if (live) {
-                                const uint32_t mk = *reinterpret_cast<const uint32_t*>(p.drop_mask + ((size_t)site * p.n_rows + grow) * L + col + 4 * j4);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) v[e] = ((mk >> (8 * e)) & 0xFFu) ? v[e] * inv_keep : 0.f;
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                v[e] = drop_keep(rm, drop_col_hash((uint32_t)(col + 4 * j4 + e), (uint32_t)site), thr) ? v[e] * inv_keep : 0.f;
-                        }
-                    }
-                    if (add_res) {
-                        const float4 r = *reinterpret_cast<const float4*>(res_row + c0 + 4 * j4);
-                        v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
-                    }
-                    if (save_res) *reinterpret_cast<float4*>(res_row + c0 + 4 * j4) = make_float4(v[0], v[1], v[2], v[3]);
-                    if (q_hi > q_lo) {  // narrow heads on this layer's output: partial dot products over my 256 columns
-#pragma unroll
-                        for (int q = 0; q < TC_HW; ++q) {
-                            if (q >= q_lo && q < q_hi) {
-                                const float4 w = *reinterpret_cast<const float4*>(hw + q * TCN + c0 + 4 * j4);
-                                hacc[q] = fmaf(v[3], w.w, fmaf(v[2], w.z, fmaf(v[1], w.y, fmaf(v[0], w.x, hacc[q]))));
-                            }
-                        }
-                    }
-                    // next layer's A operand: output column `col + 4 j4 ..` is its k index
-                    const int kcol = col + 4 * j4;
-                    float* blk = nxt + (size_t)(kcol / TCKB) * 2 * plane;
-                    const float4 h = make_float4(tc_tf32(v[0]), tc_tf32(v[1]), tc_tf32(v[2]), tc_tf32(v[3]));
-                    const float4 l = make_float4(tc_tf32(v[0] - h.x), tc_tf32(v[1] - h.y), tc_tf32(v[2] - h.z), tc_tf32(v[3] - h.w));
-                    const size_t off = tc_plane_off(tid, kcol % TCKB, TCM);
-                    *reinterpret_cast<float4*>(blk + off) = h;
-                    *reinterpret_cast<float4*>(blk + plane + off) = l;
                 }
             }
+            __syncwarp();
+            {
+                tc_epi_sync();
+                TcEpi e;
+                e.sst = sst, e.hw = hw, e.nxt = xpl[gi == 0 ? 0 : (par ^ 1)], e.res = res;
+                e.tid = row, e.grow = grow, e.site = site, e.live = live;
+                e.relu = (op.flags & MLB_F_RELU) != 0, e.add_res = (op.flags & MLB_F_ADD_RES) != 0;
+                e.save_res = (op.flags & MLB_F_SAVE_RES) != 0, e.drop = mc_drop && (op.flags & MLB_F_DROPOUT) != 0;
+                e.drop_mask = p.drop_mask, e.n_rows = p.n_rows, e.L = L;
+                e.rm = drop_row_mix(drop_seed_mix(p.drop_seed), (uint32_t)grow), e.thr = drop_threshold(p.p_drop);
+                e.inv_keep = 1.0f / (1.0f - p.p_drop);
+                mbar_wait_backoff(&done, (uint32_t)(n_done & 1), p.err_flag);
+                tmem_fence_after();
+                if (tid == 0) tmark(mk, 8 * gi + 3);
+                e.tmem_main = lane_base + (uint32_t)(TCH * half);
+                e.ccol0 = TCH * half, e.col0 = nt * TCN + TCH * half;
+                if (!head_layer) {
+                    if (e.add_res) tc_epilogue_half<0, 0, true>(e, hacc);
+                    else tc_epilogue_half<0, 0, false>(e, hacc);
+                } else if (e.add_res) {   // MonolocoModel: the last stage's output (x + y) feeds the only head
+                    const int nqg = grp_nq[hg];
+                    if (nqg <= 4) tc_epilogue_half<4, 0, true>(e, hacc);
+                    else if (nqg <= 8) tc_epilogue_half<8, 0, true>(e, hacc);
+                    else if (nqg <= 12) tc_epilogue_half<12, 0, true>(e, hacc);
+                    else tc_epilogue_half<16, 0, true>(e, hacc);
+                } else {   // (rows of this group rounded to 4, offset of the group)
+                    const int nqg = grp_nq[hg], off = grp_off[hg];
+                    if (off == 0) {
+                        if (nqg <= 4) tc_epilogue_half<4, 0, false>(e, hacc);
+                        else if (nqg <= 8) tc_epilogue_half<8, 0, false>(e, hacc);
+                        else if (nqg <= 12) tc_epilogue_half<12, 0, false>(e, hacc);
+                        else tc_epilogue_half<16, 0, false>(e, hacc);
+                    } else if (off == 4) {
+                        if (nqg <= 4) tc_epilogue_half<4, 4, false>(e, hacc);
+                        else if (nqg <= 8) tc_epilogue_half<8, 4, false>(e, hacc);
+                        else tc_epilogue_half<12, 4, false>(e, hacc);
+                    } else if (off == 8) {
+                        if (nqg <= 4) tc_epilogue_half<4, 8, false>(e, hacc);
+                        else tc_epilogue_half<8, 8, false>(e, hacc);
+                    } else {
+                        tc_epilogue_half<4, 12, false>(e, hacc);
+                    }
+                }
+                if (tid == 0) tmark(mk, 8 * gi + 4);
+            }
+            ++n_done;
             if (op.flags & MLB_F_DROPOUT) site++;
+            __syncwarp();
             tmem_fence_before();
             tc_cluster_sync();  // all column tiles of this row tile are written; TMEM reads are complete
             tmem_fence_after();
+            if (tid == 0) tmark(mk, 8 * gi + 5);
             if (gi > 0) par ^= 1;
             ++gi;
         }
 
         // ------------------------------------------------------------ tail: head partials -> CTA 0 -> decode + stores
-        {
-            const uint32_t local = smem_u32(hpart + ((size_t)nt * TCM + tid) * TC_HW);
+        if (epi_thread) {
+            const uint32_t local = smem_u32(hpart + ((size_t)(2 * nt + half) * TCM + row) * TC_HW);
             uint32_t remote;
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0u));
 #pragma unroll
@@ -380,13 +512,15 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
                              : "memory");
         }
         tc_cluster_sync();
-        if (nt == 0 && live) {
+        if (nt == 0 && live && row_owner) {
             float o[OUT_LD];
 #pragma unroll
             for (int k = 0; k < OUT_LD; ++k) o[k] = 0.f;
             for (int q = 0; q < ex.n_head_rows; ++q) {
+                const int g = (q >= grp_q0[1] && grp_n[1] > 0) ? 1 : 0;
+                const int slot = grp_off[g] + (q - grp_q0[g]);
                 float s = 0.f;
-                for (int t = 0; t < nct; ++t) s += hpart[((size_t)t * TCM + tid) * TC_HW + q];  // fixed order: deterministic
+                for (int t = 0; t < 2 * nct; ++t) s += hpart[((size_t)t * TCM + row) * TC_HW + slot];  // fixed order: deterministic
                 o[ex.head_col[q]] = s + __ldg(p.blob + ex.head_b[q]);
             }
             store_row(p, (size_t)grow, o, cenrow);
@@ -409,27 +543,24 @@ __global__ void __launch_bounds__(128, 1) loco_forward_tc_kernel(const __grid_co
 // ================================================================================================ host side
 using namespace mlb;
 
+cudaError_t mlb_tc_set_marks(unsigned long long* ptr) { return cudaMemcpyToSymbol(mlb::g_tc_marks, &ptr, sizeof(ptr)); }
+
 struct mlb_tc_state {
     float* wplanes[MLB_MAX_OPS];
     int n_kb[MLB_MAX_OPS];
     float* ws;
     size_t slot_floats;
     int max_clusters;
-    int nct;
+    int nct;     // CTAs per cluster = L / 256
 };
 
+// widths the tensor-core kernel covers: 256 output columns per CTA, clusters of up to 8 CTAs
 bool mlb_tc_supported(int L) { return L >= TCN && L % TCN == 0 && L / TCN <= TC_MAX_CT; }
-
-static cudaError_t tc_set_attr() {
-    cudaError_t e = cudaFuncSetAttribute(loco_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(loco_forward_tc_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-}
 
 static void tc_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int clusters, int nct, cudaStream_t st) {
     memset(cfg, 0, sizeof(*cfg));
     cfg->gridDim = dim3(clusters, nct);
-    cfg->blockDim = dim3(128);
+    cfg->blockDim = dim3(TC_THREADS);
     cfg->dynamicSmemBytes = TC_SMEM_BYTES;
     cfg->stream = st;
     at->id = cudaLaunchAttributeClusterDimension;
@@ -443,7 +574,7 @@ mlb_tc_state* mlb_tc_prepare(const float* blob_dev, const mlb_op* ops, int n_ops
     mlb_tc_state* t = new mlb_tc_state();
     memset(t, 0, sizeof(*t));
     t->nct = L / TCN;
-    *err = tc_set_attr();
+    *err = cudaFuncSetAttribute(loco_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (*err != cudaSuccess) { delete t; return nullptr; }
     int first = -1;
     for (int i = 0; i < n_ops; ++i) {
@@ -462,6 +593,7 @@ mlb_tc_state* mlb_tc_prepare(const float* blob_dev, const mlb_op* ops, int n_ops
         cudaGetLastError();
         n = 148 / t->nct / 2;
     }
+    if (getenv("MLB_TC_CLUSTERS") && atoi(getenv("MLB_TC_CLUSTERS")) > 0 && atoi(getenv("MLB_TC_CLUSTERS")) < n) n = atoi(getenv("MLB_TC_CLUSTERS"));
     t->max_clusters = n;
     const size_t plane = (size_t)TCM * TCKB;
     t->slot_floats = (size_t)t->n_kb[first] * 2 * plane + 2 * (size_t)(L / TCKB) * 2 * plane + (size_t)TCM * L;
@@ -489,6 +621,7 @@ int mlb_tc_clusters(const mlb_tc_state* t, int n_rows) {
     const int tiles = (n_rows + TCM - 1) / TCM;
     return tiles < t->max_clusters ? tiles : t->max_clusters;
 }
+int mlb_tc_max_clusters(const mlb_tc_state* t) { return t->max_clusters; }
 
 cudaError_t mlb_tc_launch(const mlb_tc_state* t, const FwdParams& p, cudaStream_t st) {
     TcExtra ex;

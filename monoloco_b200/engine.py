@@ -84,6 +84,11 @@ class LocoEngine:
         except Exception:  # interpreter shutdown
             pass
 
+    def last_kernel(self):
+        """(id, name) of the kernel the most recent forward launched."""
+        k = self._lib.mlb_last_kernel(self._h)
+        return k, L_.KERNEL_NAMES.get(k, '?')
+
     def check_error(self):
         """Raise if a kernel of this engine reported a protocol time-out (call after a stream synchronisation)."""
         err = self._lib.mlb_device_error(self._h)

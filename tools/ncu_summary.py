@@ -20,7 +20,11 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct',
         'l1tex__m_xbar2l1tex_read_bytes.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-        'smsp__inst_executed.sum', 'smsp__inst_executed_op_tma_ld.sum', 'sass__inst_executed_shared_loads']
+        'smsp__inst_executed.sum', 'smsp__inst_executed_op_tma_ld.sum', 'sass__inst_executed_shared_loads',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_tensor.sum', 'lts__t_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__m_l1tex2xbar_write_bytes.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__cycles_active.avg']
 out = {k: {'value': m[k][0], 'unit': m[k][1]} for k in want if k in m}
 
 
