@@ -151,12 +151,30 @@ struct TcEpi {            // what one epilogue pass over a 128-column half needs
     int col0;             // first global column of the half
     int ccol0;            // first CTA-local column of the half (0 or 128)
     int tid, grow, site;
-    bool live, relu, add_res, save_res, drop;
+    bool live, relu, add_res, save_res, drop, write_planes;
     const uint8_t* drop_mask;
     int n_rows, L;
     uint32_t rm, thr;
     float inv_keep;
+    uint64_t keep;        // L2 evict_last policy for the residual
 };
+
+// The fp32 residual of a stage is written two layers before it is read: ~110 MB of other L2 traffic pass in between and
+// plain LRU had evicted it to HBM by then (100 MB of DRAM round trips per batch of 4096).  L2::evict_last keeps it resident.
+__device__ __forceinline__ uint64_t tc_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tc_st_keep(float* ptr, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ float4 tc_ld_keep(const float* ptr, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+}
 
 // MC-dropout of four consecutive columns (rare path, kept out of line: the epilogue loops must stay small enough for the
 // instruction cache -- fully unrolled they were 140 KB per instantiation and every first use cost ~15 us of code fetch)
@@ -208,18 +226,20 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcEpi& e, int ch, const 
             const float4 r = rr[j4];
             v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
         }
-        if (e.save_res) *reinterpret_cast<float4*>(rq) = make_float4(v[0], v[1], v[2], v[3]);
+        if (e.save_res) tc_st_keep(rq, make_float4(v[0], v[1], v[2], v[3]), e.keep);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {   // narrow heads on this layer's output: partial dot products over my columns
             const float4 w = *reinterpret_cast<const float4*>(e.hw + q * TCN + lc);
             hacc[OFF + q] = fmaf(v[3], w.w, fmaf(v[2], w.z, fmaf(v[1], w.y, fmaf(v[0], w.x, hacc[OFF + q]))));
         }
-        float* blk = e.nxt + (size_t)(gc / TCKB) * 2 * plane;
-        const float4 h = make_float4(tc_tf32(v[0]), tc_tf32(v[1]), tc_tf32(v[2]), tc_tf32(v[3]));
-        const float4 l = make_float4(tc_tf32(v[0] - h.x), tc_tf32(v[1] - h.y), tc_tf32(v[2] - h.z), tc_tf32(v[3] - h.w));
-        const size_t off = tc_plane_off(e.tid, gc % TCKB);
-        *reinterpret_cast<float4*>(blk + off) = h;
-        *reinterpret_cast<float4*>(blk + plane + off) = l;
+        if (e.write_planes) {   // the last layer's output only feeds the heads
+            float* blk = e.nxt + (size_t)(gc / TCKB) * 2 * plane;
+            const float4 h = make_float4(tc_tf32(v[0]), tc_tf32(v[1]), tc_tf32(v[2]), tc_tf32(v[3]));
+            const float4 l = make_float4(tc_tf32(v[0] - h.x), tc_tf32(v[1] - h.y), tc_tf32(v[2] - h.z), tc_tf32(v[3] - h.w));
+            const size_t off = tc_plane_off(e.tid, gc % TCKB);
+            *reinterpret_cast<float4*>(blk + off) = h;
+            *reinterpret_cast<float4*>(blk + plane + off) = l;
+        }
     }
 }
 
@@ -237,7 +257,7 @@ __device__ __forceinline__ void tc_epilogue_half(const TcEpi& e, float* hacc) {
         if (ADD) {
 #pragma unroll
             for (int j4 = 0; j4 < TC_CW / 4; ++j4)
-                rr[j4] = *reinterpret_cast<const float4*>(res_row + (size_t)(ch * (TC_CW / 4) + j4) * TCM * 4);
+                rr[j4] = tc_ld_keep(res_row + (size_t)(ch * (TC_CW / 4) + j4) * TCM * 4, e.keep);
         }
     };
     fetch(0, mb0, cb0, rr0);
@@ -300,6 +320,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __
         if (grp_n[g] == 0) grp_src[g] = ex.head_src[q], grp_q0[g] = q;
         grp_n[g]++;
     }
+    int n_gemm = 0;
+    for (int oi = 0; oi < p.n_ops; ++oi) n_gemm += p.ops[oi].type == MLB_OP_GEMM;
     const int grp_nq[2] = {(grp_n[0] + 3) & ~3, (grp_n[1] + 3) & ~3};
     const int grp_off[2] = {0, grp_nq[0]};
 
@@ -452,9 +474,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __
                 e.tid = row, e.grow = grow, e.site = site, e.live = live;
                 e.relu = (op.flags & MLB_F_RELU) != 0, e.add_res = (op.flags & MLB_F_ADD_RES) != 0;
                 e.save_res = (op.flags & MLB_F_SAVE_RES) != 0, e.drop = mc_drop && (op.flags & MLB_F_DROPOUT) != 0;
+                e.write_planes = gi + 1 < n_gemm;
                 e.drop_mask = p.drop_mask, e.n_rows = p.n_rows, e.L = L;
                 e.rm = drop_row_mix(drop_seed_mix(p.drop_seed), (uint32_t)grow), e.thr = drop_threshold(p.p_drop);
                 e.inv_keep = 1.0f / (1.0f - p.p_drop);
+                e.keep = tc_policy_evict_last();
                 mbar_wait_backoff(&done, (uint32_t)(n_done & 1), p.err_flag);
                 tmem_fence_after();
                 if (tid == 0) tmark(mk, 8 * gi + 3);
@@ -496,6 +520,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __
             tc_cluster_sync();  // all column tiles of this row tile are written; TMEM reads are complete
             tmem_fence_after();
             if (tid == 0) tmark(mk, 8 * gi + 5);
+            // The planes this layer read are dead now (every CTA of the cluster is past its MMAs) and will be fully
+            // rewritten before their next use: drop the dirty lines from L2 instead of letting them be written back to
+            // HBM (discard.global.L2; without it the workspace churn was 255 MB of DRAM writes per batch of 4096).
+            {
+                const size_t lines = (size_t)n_kb * 2 * TC_A_PLANE / 128;   // 128-byte lines; CTA nt takes lines nt, nt + nct, ...
+                const unsigned char* base = reinterpret_cast<const unsigned char*>(xsrc_f);
+                for (size_t ln = (size_t)nt + (size_t)nct * tid; ln < lines; ln += (size_t)nct * TC_THREADS)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + ln * 128) : "memory");
+                if ((op.flags & MLB_F_ADD_RES) && !(op.flags & MLB_F_SAVE_RES)) {   // last use of the stage residual
+                    const unsigned char* rb = reinterpret_cast<const unsigned char*>(res + (size_t)(nt * TCN / 4) * TCM * 4);
+                    for (size_t o = (size_t)tid * 128; o < (size_t)TCN * TCM * 4; o += (size_t)TC_THREADS * 128)
+                        asm volatile("discard.global.L2 [%0], 128;" ::"l"(rb + o) : "memory");
+                }
+            }
             if (gi > 0) par ^= 1;
             ++gi;
         }
