@@ -145,3 +145,25 @@ def test_torch_port_train_step(mode, auto):
             assert np.allclose(sd[k[4:]].detach().numpy(), f[k], rtol=1e-5, atol=1e-6), k
     if auto:
         assert np.allclose(ls.grad.numpy(), f['grad.log_sigmas'], rtol=1e-5)
+
+
+def test_reference_laplace_sampler_is_laplace_mu_b():
+    """The distribution our device sampler must reproduce (process.py:101-122): the live reference's 100 draws per (mu, b)
+    pass a Kolmogorov-Smirnov test against Laplace(mu, scale=b) -- and fail it against the neighbouring hypotheses
+    (scale b / sqrt(2), i.e. "b is the std", and scale 2 b) when the three columns are pooled after standardisation."""
+    f = np.load(os.path.join(GOLDEN, 'ref_laplace_sampling.npz'))
+    mu, b, xs = f['mu_bi'][:, 0].astype(np.float64), f['mu_bi'][:, 1].astype(np.float64), f['samples'].astype(np.float64)
+
+    def ks(z):   # KS distance of standardised draws z = (x - mu) / scale against Laplace(0, 1)
+        z = np.sort(z)
+        cdf = np.where(z < 0, 0.5 * np.exp(z), 1 - 0.5 * np.exp(-z))
+        n = len(z)
+        return max(np.max(np.arange(1, n + 1) / n - cdf), np.max(cdf - np.arange(0, n) / n))
+
+    crit = 1.63 / np.sqrt(xs.shape[0])   # alpha = 0.01
+    for j in range(3):
+        assert ks((xs[:, j] - mu[j]) / b[j]) < crit, j
+    pooled = lambda s: np.concatenate([(xs[:, j] - mu[j]) / (s * b[j]) for j in range(3)])  # noqa: E731
+    crit3 = 1.63 / np.sqrt(3 * xs.shape[0])
+    assert ks(pooled(1.0)) < crit3
+    assert ks(pooled(1 / np.sqrt(2))) > crit3 and ks(pooled(2.0)) > crit3
