@@ -579,6 +579,7 @@ def main():
             # string asks for is nested beside it
             "roofline": roof,
         }
+        line["kernel_selection"] = eng.kernel_times()
         line.update(multi)
         if not args.no_extras and world == 1:
             line["extras"] = extras(eng, sd, dev, flush, ffma_peak)

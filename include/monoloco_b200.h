@@ -85,6 +85,10 @@ enum { MLB_KERNEL_TILE = 0,    /* loco_forward_kernel: one CTA per row tile, FFM
        MLB_KERNEL_WIDE = 2,    /* loco_forward_wide_kernel: the whole grid on <= 32 rows                        */
        MLB_KERNEL_TC = 3       /* loco_forward_tc_kernel: tcgen05 kind::tf32, 3 MMAs per fp32 product           */ };
 int mlb_last_kernel(mlb_handle h);
+/* per-wave kernel times measured on this device when the handle was created (ms): [0] one wave of FFMA clusters, [1] + [2] * TM
+ * one wave of FFMA row tiles, [3] one wave of tensor-core tiles -- mlb_forward picks the kernel family with them (no constants
+ * from another box).  Returns 1 if measured, 0 if the defaults are in use (MLB_NO_CALIBRATE). */
+int mlb_kernel_times(mlb_handle h, double out_ms[4]);
 /* co-resident clusters of the tensor-core kernel on this device (= its persistent grid size), 0 if unavailable */
 int mlb_tc_resident_clusters(mlb_handle h);
 /* device error word of this handle (mapped host memory; read it after a stream synchronisation): 0 = none,

@@ -21,7 +21,7 @@ FWD_FORCE_TC = 128
 KERNEL_NAMES = {0: 'loco_forward_kernel (FFMA2 row tiles)', 1: 'loco_forward_cluster_kernel (FFMA2, 8-CTA clusters)',
                 2: 'loco_forward_wide_kernel (FFMA, whole grid)', 3: 'loco_forward_tc_kernel (tcgen05 3xTF32)'}
 
-EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error', 'mlb_last_kernel', 'mlb_tc_resident_clusters',
+EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error', 'mlb_last_kernel', 'mlb_tc_resident_clusters', 'mlb_kernel_times',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_post_process', 'mlb_kitti_rows', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',
            'mlb_train_forward', 'mlb_train_backward', 'mlb_train_step', 'mlb_train_phase_times', 'mlb_train_subphase_times',
            'mlb_adam_clip_step',
@@ -106,6 +106,7 @@ def lib():
     l.mlb_device_error.argtypes = [C.c_void_p]
     l.mlb_last_kernel.argtypes = [C.c_void_p]
     l.mlb_tc_resident_clusters.argtypes = [C.c_void_p]
+    l.mlb_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     l.mlb_forward.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_forward_host.argtypes = [C.c_void_p, C.POINTER(MlbForwardArgs), C.c_void_p]
     l.mlb_preprocess.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p, C.c_void_p]

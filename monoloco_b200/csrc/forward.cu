@@ -477,7 +477,9 @@ __global__ void laplace_std_kernel(const float* __restrict__ d_bi, int n_pass, i
         const float b = fabsf(d_bi[((size_t)n * n_rows + row) * 2 + 1]);  // process.py:105
         for (int s = 0; s < n_samples; ++s) {
             const uint32_t r = mix32((((uint64_t)row << 32) | ((uint64_t)n << 16) | (uint64_t)s) ^ (seed * 0x9E3779B97F4A7C15ULL));
-            const float u = ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f) - 0.5f;  // (-0.5, 0.5)
+            // 23 random bits: (r >> 9) + 0.5 is exact in fp32, so u stays strictly inside (-0.5, 0.5); with 24 bits the top
+            // value rounded up to u = 0.5 -> log1p(-1) = -inf -> NaN std once per 2^24 draws (found by the 200k-draw test)
+            const float u = ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f) - 0.5f;
             const float x = mu - b * copysignf(1.f, u) * log1pf(-2.f * fabsf(u));
             ++cnt;
             const double dlt = (double)x - mean;
@@ -584,6 +586,9 @@ struct mlb_model {
     size_t res_floats;
     mlb_tc_state* tc;              // tensor-core kernel state (weight planes, cluster workspace), or null
     int last_kernel;               // MLB_KERNEL_* of the most recent mlb_forward launch
+    // per-wave times measured on this device at mlb_create (ms): FFMA cluster wave, row-tile wave = a + b * TM, tensor-core wave
+    double t_cluster_wave, t_tile_a, t_tile_b, t_tc_wave;
+    bool calibrated;
     bool ffma_ok;                  // the FFMA kernels fit this width (L <= 1024)
     int tc_min_rows;               // batches of at least this many rows go to the tensor-core kernel
     unsigned* gather_done;         // monotonic count of CTAs that finished their peer stores (fused all-gather)
@@ -644,6 +649,9 @@ static size_t fwd_smem_bytes(int L) {
     size_t fl = (size_t)L * MP + MP * OUT_LD + MP * 4 + (size_t)NSTAGE * KC * L;
     return fl * sizeof(float) + 2 * NSTAGE * sizeof(uint64_t) + 16;
 }
+
+static void calibrate(mlb_handle h);
+static int pick_rows_per_group(int n_rows, int n_ctas);
 
 extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const float* packed_host, size_t n_floats,
                           int device, mlb_handle* out) {
@@ -733,8 +741,60 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
     CU(cudaHostAlloc(reinterpret_cast<void**>(&m->err_flag_host), sizeof(int), cudaHostAllocMapped));
     *m->err_flag_host = 0;
     CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->err_flag_dev), m->err_flag_host, 0));
+    calibrate(m);
     *out = m;
     return 0;
+}
+
+// Time one wave of every kernel family on THIS device (CUDA events, L2 warm, 2 launches each, the second one counts) so that
+// the batch-size thresholds of mlb_forward are measured quantities instead of constants from another box.  ~10 launches.
+static void calibrate(mlb_handle h) {
+    const mlb_model_desc& d = h->desc;
+    h->t_cluster_wave = 0.185, h->t_tile_a = 0.42, h->t_tile_b = 0.067, h->t_tc_wave = 0.33;  // round-2 B200 defaults
+    if (getenv("MLB_NO_CALIBRATE")) return;
+    const int max_rows = h->n_sms * 32;
+    float *x = nullptr, *raw = nullptr;
+    if (cudaMalloc(&x, (size_t)max_rows * d.input_size * sizeof(float)) != cudaSuccess) return;
+    if (cudaMalloc(&raw, (size_t)max_rows * d.output_size * sizeof(float)) != cudaSuccess) { cudaFree(x); return; }
+    cudaMemset(x, 0, (size_t)max_rows * d.input_size * sizeof(float));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    auto time_one = [&](int rows, int flags, int tm) -> double {
+        mlb_forward_args a;
+        memset(&a, 0, sizeof(a));
+        a.input_kind = MLB_IN_X, a.flags = flags, a.n_rows = rows, a.rows_per_group = tm, a.x = x, a.out_raw = raw;
+        float ms = -1.f;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0, 0);
+            if (mlb_forward(h, &a, nullptr) != 0) return -1.0;
+            cudaEventRecord(e1, 0);
+            if (cudaEventSynchronize(e1) != cudaSuccess) return -1.0;
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        return (double)ms;
+    };
+    if (h->ffma_ok) {
+        const double t8 = time_one(h->n_sms * 16, MLB_FWD_FORCE_TILE, 8), t16 = time_one(h->n_sms * 32, MLB_FWD_FORCE_TILE, 16);
+        if (t8 > 0 && t16 > t8) h->t_tile_b = (t16 - t8) / 8.0, h->t_tile_a = t8 - 8.0 * h->t_tile_b;
+        if (h->slab_dev != nullptr) {
+            const double tc = time_one(h->small_conc * 16, MLB_FWD_FORCE_CLUSTER, 0);
+            if (tc > 0) h->t_cluster_wave = tc;
+        }
+    }
+    if (h->tc != nullptr) {
+        const double tt = time_one(128, MLB_FWD_FORCE_TC, 0);
+        if (tt > 0) h->t_tc_wave = tt;
+    }
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+    cudaFree(x), cudaFree(raw);
+    cudaGetLastError();
+    h->calibrated = true;
+}
+
+extern "C" int mlb_kernel_times(mlb_handle h, double out_ms[4]) {
+    if (!h || !out_ms) return fail("mlb_kernel_times: null argument");
+    out_ms[0] = h->t_cluster_wave, out_ms[1] = h->t_tile_a, out_ms[2] = h->t_tile_b, out_ms[3] = h->t_tc_wave;
+    return h->calibrated ? 1 : 0;
 }
 
 extern "C" int mlb_update_weights(mlb_handle h, const float* packed_host, size_t n_floats, void* stream) {
@@ -883,7 +943,22 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     if ((a->flags & MLB_FWD_FORCE_TC) && h->tc == nullptr)
         return fail("mlb_forward: the tensor-core kernel is not available for this model (linear_size % 256 != 0)");
     if (!h->ffma_ok && forced_ffma) return fail("mlb_forward: this model width runs on the tensor-core kernel only");
-    if (h->tc != nullptr && ((a->flags & MLB_FWD_FORCE_TC) || !h->ffma_ok || (!forced_ffma && a->n_rows >= h->tc_min_rows))) {
+    bool pick_tc = false;
+    if (h->tc != nullptr && !forced_ffma && h->ffma_ok && a->n_rows > 64) {
+        // measured wave times (calibrate()): tensor-core waves of 128-row tiles against the better of FFMA clusters / row tiles
+        const int tc_cl = mlb_tc_clusters(h->tc, 1 << 30);
+        const long tc_tiles = (a->n_rows + 127) / 128;
+        const double t_tc = h->t_tc_wave * (double)((tc_tiles + tc_cl - 1) / tc_cl);
+        double t_ffma = 1e30;
+        if (h->slab_dev != nullptr) t_ffma = h->t_cluster_wave * (double)(((a->n_rows + 15) / 16 + h->small_conc - 1) / h->small_conc);
+        const int tmc = pick_rows_per_group(a->n_rows, h->n_sms);
+        const long tl = (a->n_rows + 2 * tmc - 1) / (2 * tmc);
+        const double t_tl = (h->t_tile_a + h->t_tile_b * tmc) * (double)((tl + h->n_sms - 1) / h->n_sms);
+        if (t_tl < t_ffma) t_ffma = t_tl;
+        pick_tc = t_tc < t_ffma;
+        if (getenv("MLB_TC_MIN_ROWS")) pick_tc = a->n_rows >= h->tc_min_rows;
+    }
+    if (h->tc != nullptr && ((a->flags & MLB_FWD_FORCE_TC) || !h->ffma_ok || pick_tc)) {
         p.flags &= ~MLB_FWD_RES_TMEM;
         arm_gather((unsigned)mlb_tc_clusters(h->tc, a->n_rows));  // one arrival per cluster leader
         cudaError_t et = mlb_tc_launch(h->tc, p, st);
@@ -931,14 +1006,14 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
     }
 
     // ---- small batches: 8-CTA cluster per 16 detections (forward_small.cu) when that finishes sooner than row tiles.
-    // Cost model (measured): cluster wave 0.18 ms for `small_conc` clusters; tile wave 0.42 + 0.067 TM ms.
+    // Cost model, measured on this device at mlb_create (calibrate()): cluster wave for `small_conc` clusters; tile wave a + b TM.
     if (h->slab_dev != nullptr && !(a->flags & MLB_FWD_FORCE_TILE)) {
         const int n_clusters = (a->n_rows + 15) / 16;
         const int conc = h->small_conc;
-        const double t_small = 0.185 * ((n_clusters + conc - 1) / conc);
+        const double t_small = h->t_cluster_wave * ((n_clusters + conc - 1) / conc);
         const int tm0 = pick_rows_per_group(a->n_rows, h->n_sms);
         const long tiles0 = (a->n_rows + 2 * tm0 - 1) / (2 * tm0);
-        const double t_tile = (0.42 + 0.067 * tm0) * ((tiles0 + h->n_sms - 1) / h->n_sms);
+        const double t_tile = (h->t_tile_a + h->t_tile_b * tm0) * ((tiles0 + h->n_sms - 1) / h->n_sms);
         if ((a->flags & MLB_FWD_FORCE_CLUSTER) || (a->rows_per_group == 0 && t_small < t_tile)) {
             p.n_tiles = n_clusters;
             arm_gather((unsigned)(n_clusters < conc ? n_clusters : conc));  // one arrival per cluster leader

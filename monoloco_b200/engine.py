@@ -89,6 +89,14 @@ class LocoEngine:
         k = self._lib.mlb_last_kernel(self._h)
         return k, L_.KERNEL_NAMES.get(k, '?')
 
+    def kernel_times(self):
+        """Per-wave kernel times measured at engine creation (ms) and the tensor-core cluster count: what mlb_forward's
+        kernel choice is based on."""
+        t = (C.c_double * 4)()
+        measured = self._lib.mlb_kernel_times(self._h, t)
+        return {'measured': bool(measured), 'ffma_cluster_wave_ms': t[0], 'ffma_tile_wave_ms': '%.4f + %.4f * TM' % (t[1], t[2]),
+                'tc_wave_ms': t[3], 'tc_resident_clusters': self._lib.mlb_tc_resident_clusters(self._h)}
+
     def check_error(self):
         """Raise if a kernel of this engine reported a protocol time-out (call after a stream synchronisation)."""
         err = self._lib.mlb_device_error(self._h)

@@ -1,7 +1,8 @@
 """GPU: the fused training step (forward + multi-task Laplace loss + backward) against the live-reference fixtures
 (tests/golden/ref_train_*.npz: loss, per-task values, every parameter gradient, running-stat update) and against the
 torch-autograd oracle (oracle/torch_port.py) at larger sizes with explicit dropout masks.
-Gradient rule: |a-b| <= 1e-4*|b| + 2e-5*max|b| + 2e-7 per tensor and relative L2 <= 2e-5."""
+Gradient rule: |a-b| <= 1e-4*|b| + 2e-5*max|b| + 2e-7 per tensor and relative L2 <= 1e-5; the oracle's own
+fp32 self-noise is measured in profiles/r2_grad_noise.md (9e-7 at these sizes, 2e-3 at batch 4096 x 1024)."""
 import os
 
 import numpy as np
@@ -30,7 +31,7 @@ def _cmp_grad(name, got, ref):
     assert (err <= 1e-4 * np.abs(ref) + 2e-5 * scale + 2e-7).all(), (name, float(err.max()), scale)
     nrm = float(np.linalg.norm(ref))
     if nrm > 1e-5 * np.sqrt(ref.size):
-        assert float(np.linalg.norm(got - ref)) / nrm <= float(os.environ.get("MLB_GRAD_RELL2", "2e-5")), (name, float(np.linalg.norm(got - ref)) / nrm)
+        assert float(np.linalg.norm(got - ref)) / nrm <= float(os.environ.get("MLB_GRAD_RELL2", "1e-5")), (name, float(np.linalg.norm(got - ref)) / nrm)
 
 
 TASKS = {'mono': ('d', 'x', 'y', 'h', 'w', 'l', 'ori'), 'stereo': ('d', 'x', 'y', 'h', 'w', 'l', 'ori', 'aux')}
