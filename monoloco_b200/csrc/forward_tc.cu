@@ -561,7 +561,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __
                 for (int t = 0; t < 2 * nct; ++t) s += hpart[((size_t)t * TCM + row) * TC_HW + slot];  // fixed order: deterministic
                 o[ex.head_col[q]] = s + __ldg(p.blob + ex.head_b[q]);
             }
-            store_row(p, (size_t)grow, o, cenrow);
+            store_row(p, (size_t)grow, o, cenrow, p.n_gather ? hw + (size_t)row * MLB_GATHER_LD : nullptr);
+        }
+        if (nt == 0 && p.n_gather) {
+            // fused all-gather: the tile's rows ([<=128][20] floats, contiguous in every gather buffer) leave as coalesced
+            // 16-byte stores -- 128-byte NVLink packets instead of 11 scattered 4..16-byte stores per row and peer
+            // (`hw` is free here: the head layers are done; it is re-staged in the next tile's first head layer)
+            __syncthreads();
+            const int rows_live = min(TCM, p.n_rows - rb * TCM);
+            const int n4 = rows_live * (MLB_GATHER_LD / 4);
+            const float4* src = reinterpret_cast<const float4*>(hw);
+            for (int pg = 0; pg < p.n_gather; ++pg) {
+                float4* dst = reinterpret_cast<float4*>(p.gather[pg] + (size_t)(p.gather_row0 + (long long)rb * TCM) * MLB_GATHER_LD);
+                for (int i = tid; i < n4; i += TC_THREADS) dst[i] = src[i];
+            }
+            __threadfence_system();  // peer stores ordered before this CTA's arrival in gather_finish()
+            __syncthreads();
         }
         // the next tile's prologue ends with a cluster barrier: CTA 0 has finished reading hpart before any peer writes it
         // again, and before its own producer refills the ring that hpart aliases (program order + fence.proxy.async)

@@ -177,7 +177,10 @@ __device__ __forceinline__ void stage_input_tile(const FwdParams& p, int row0, i
 }
 
 // One decoded row -> the caller's outputs (raw, decoded, xyz of the bbox-centre ray, fused all-gather peers).
-__device__ __forceinline__ void store_row(const FwdParams& p, size_t grow, const float* o, const float* cen_row) {
+// gather_stage != nullptr: instead of storing the gather row to the peers itself, the row ([MLB_GATHER_LD] floats) is left
+// there (shared memory) and the caller ships the whole tile with coalesced stores.
+__device__ __forceinline__ void store_row(const FwdParams& p, size_t grow, const float* o, const float* cen_row,
+                                          float* gather_stage = nullptr) {
     for (int k = 0; k < p.out_size; ++k) p.out_raw[grow * p.out_size + k] = o[k];
     float x, y, z, d, bi, yaw_p, yaw_o, aux;
     decode_row(p.decode_kind, p.out_size, o, x, y, z, d, bi, yaw_p, yaw_o, aux);
@@ -186,7 +189,12 @@ __device__ __forceinline__ void store_row(const FwdParams& p, size_t grow, const
         dst[0] = make_float4(x, y, z, d);
         dst[1] = make_float4(bi, yaw_p, yaw_o, aux);
     }
-    for (int pg = 0; pg < p.n_gather; ++pg) {  // the same row straight into every rank's gather buffer over NVLink
+    if (gather_stage != nullptr) {
+        for (int k = 0; k < MLB_GATHER_DEC; ++k) gather_stage[k] = k < p.out_size ? o[k] : 0.f;
+        reinterpret_cast<float4*>(gather_stage + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
+        reinterpret_cast<float4*>(gather_stage + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
+    }
+    for (int pg = 0; gather_stage == nullptr && pg < p.n_gather; ++pg) {  // the same row straight into every rank's gather buffer over NVLink
         float* dst = p.gather[pg] + (size_t)(p.gather_row0 + (long long)grow) * MLB_GATHER_LD;
         for (int k = 0; k < p.out_size; ++k) dst[k] = o[k];
         reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
