@@ -236,7 +236,7 @@ def extras(eng, sd, dev, flush, ffma_peak):
         cold, cold_min = timed(lambda: eng.forward(x16, kk=kk, kind=L_.IN_KPS), 20, dev, flush=flush)
         warm = lat["16"]["ms"]
         out["small_batch_roofline"] = {
-            "rows": 16, "kernel": "loco_forward_wide_kernel", "bound": "hbm", "weight_bytes": wbytes,
+            "rows": 16, "kernel": eng.last_kernel()[1], "bound": "hbm", "weight_bytes": wbytes,
             "cold_ms": cold, "cold_min_ms": cold_min, "cold_GBps": wbytes / (cold * 1e-3) / 1e9,
             "cold_frac_of_hbm_copy_peak": wbytes / (cold * 1e-3) / 1e9 / hbm_peak,
             "warm_ms": warm, "warm_GBps": wbytes / (warm * 1e-3) / 1e9,

@@ -83,7 +83,8 @@ int mlb_num_sms(mlb_handle h);
 enum { MLB_KERNEL_TILE = 0,    /* loco_forward_kernel: one CTA per row tile, FFMA2                              */
        MLB_KERNEL_CLUSTER = 1, /* loco_forward_cluster_kernel: 8-CTA cluster per 16 rows, FFMA2                 */
        MLB_KERNEL_WIDE = 2,    /* loco_forward_wide_kernel: the whole grid on <= 32 rows                        */
-       MLB_KERNEL_TC = 3       /* loco_forward_tc_kernel: tcgen05 kind::tf32, 3 MMAs per fp32 product           */ };
+       MLB_KERNEL_TC = 3,      /* loco_forward_tc_kernel: tcgen05 kind::tf32, 3 MMAs per fp32 product           */
+       MLB_KERNEL_WIDE2 = 4    /* loco_forward_wide2_kernel: 4-CTA clusters, K x N split, <= 16 rows            */ };
 int mlb_last_kernel(mlb_handle h);
 /* per-wave kernel times measured on this device when the handle was created (ms): [0] one wave of FFMA clusters, [1] + [2] * TM
  * one wave of FFMA row tiles, [3] one wave of tensor-core tiles -- mlb_forward picks the kernel family with them (no constants
@@ -108,7 +109,8 @@ enum { MLB_FWD_ZERO_CENTER = 1, /* preprocess_monoloco(zero_center=True) (net.py
        MLB_FWD_FORCE_CLUSTER = 16, /* always use the small-batch kernel (8-CTA cluster per 16 rows)  */
        MLB_FWD_RES_SCRATCH   = 32, /* stash the residual in the L2-resident global scratch instead   */
        MLB_FWD_FORCE_WIDE    = 64, /* always use the whole-grid latency kernel (one launch / 32 rows)*/
-       MLB_FWD_FORCE_TC      = 128 /* always use the tensor-core kernel (error-compensated TF32, 128-row tiles) */ };
+       MLB_FWD_FORCE_TC      = 128, /* always use the tensor-core kernel (error-compensated TF32, 128-row tiles) */
+       MLB_FWD_FORCE_WIDE2   = 256  /* always use the second-generation latency kernel (<= 16 rows)             */ };
 
 typedef struct mlb_forward_args {
     int32_t input_kind;     /* MLB_IN_*                                                             */

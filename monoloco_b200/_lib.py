@@ -18,8 +18,10 @@ DECODE_NONE, DECODE_LOCO, DECODE_MONO, DECODE_DB = 0, 1, 2, 3
 IN_X, IN_KPS, IN_KPS_STEREO = 0, 1, 2
 FWD_ZERO_CENTER, FWD_DROPOUT, FWD_RES_TMEM, FWD_FORCE_TILE, FWD_FORCE_CLUSTER, FWD_RES_SCRATCH, FWD_FORCE_WIDE = 1, 2, 4, 8, 16, 32, 64
 FWD_FORCE_TC = 128
+FWD_FORCE_WIDE2 = 256
 KERNEL_NAMES = {0: 'loco_forward_kernel (FFMA2 row tiles)', 1: 'loco_forward_cluster_kernel (FFMA2, 8-CTA clusters)',
-                2: 'loco_forward_wide_kernel (FFMA, whole grid)', 3: 'loco_forward_tc_kernel (tcgen05 3xTF32)'}
+                2: 'loco_forward_wide_kernel (FFMA, whole grid)', 3: 'loco_forward_tc_kernel (tcgen05 3xTF32)',
+                4: 'loco_forward_wide2_kernel (FFMA, 4-CTA clusters, K x N split)'}
 
 EXPORTS = ['mlb_create', 'mlb_update_weights', 'mlb_destroy', 'mlb_last_error', 'mlb_abi_version', 'mlb_num_sms', 'mlb_device_error', 'mlb_last_kernel', 'mlb_tc_resident_clusters', 'mlb_kernel_times',
            'mlb_forward', 'mlb_forward_host', 'mlb_preprocess', 'mlb_stereo_filter', 'mlb_post_process', 'mlb_kitti_rows', 'mlb_decode', 'mlb_laplace_std', 'mlb_ipc_alloc', 'mlb_ipc_open', 'mlb_ipc_close', 'mlb_ipc_free', 'mlb_train_create', 'mlb_train_destroy',

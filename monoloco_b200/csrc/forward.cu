@@ -547,6 +547,16 @@ size_t mlb_small_smem_bytes(int L);
 cudaError_t mlb_small_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, long long* slab_off, cudaStream_t st);
 cudaError_t mlb_small_launch(const FwdParams& p, const float* slab, const long long* slab_off, int n_clusters, cudaStream_t st);
 int mlb_small_max_clusters(int L);
+// forward_wide2.cu
+size_t mlb_wide2_slab_floats(const mlb_op* ops, int n_ops, int L, long long* slab_off);
+cudaError_t mlb_wide2_pack(const float* blob, const mlb_op* ops, int n_ops, int L, float* slab, const long long* slab_off, cudaStream_t st);
+bool mlb_wide2_supported(const mlb_op* ops, int n_ops, int L, int out_size, int n_sms);
+int mlb_wide2_epochs(const mlb_op* ops, int n_ops);
+size_t mlb_wide2_xg_pairs(int L);
+size_t mlb_wide2_hg_pairs(int L);
+cudaError_t mlb_wide2_set_marks(unsigned long long* ptr);
+cudaError_t mlb_wide2_launch(const FwdParams& p, const float* wslab, const long long* wslab_off, unsigned long long* xg,
+                             unsigned long long* hg, unsigned epoch_base, cudaStream_t st);
 // forward_tc.cu
 struct mlb_tc_state;
 bool mlb_tc_supported(int L);
@@ -582,6 +592,12 @@ struct mlb_model {
     unsigned* wide_bar;            // monotonic grid-barrier counter
     unsigned wide_bar_count;       // host copy of the counter after the launches issued so far
     bool wide_disabled;            // a cooperative launch was refused once: stay on the other kernels
+    float* w2slab_dev;             // [cluster][K slice] slabs for the second-generation latency kernel (forward_wide2.cu), or null
+    long long w2slab_off[MLB_MAX_OPS];
+    unsigned long long* wide2_xg;  // (value, epoch) exchange pairs
+    unsigned long long* wide2_hg;  // head partial pairs
+    unsigned wide2_epoch;          // epochs consumed by the launches issued so far
+    bool wide2_disabled;
     float* res_scratch;
     size_t res_floats;
     mlb_tc_state* tc;              // tensor-core kernel state (weight planes, cluster workspace), or null
@@ -634,6 +650,7 @@ extern "C" int mlb_debug_fwd_marks(void* dev_buf) {
     cudaError_t e = cudaMemcpyToSymbol(mlb::g_fwd_marks, &ptr, sizeof(ptr));
     if (e == cudaSuccess) e = mlb_wide_set_marks(ptr);
     if (e == cudaSuccess) e = mlb_tc_set_marks(ptr);
+    if (e == cudaSuccess) e = mlb_wide2_set_marks(ptr);
     if (e != cudaSuccess) {
         g_mlb_err = std::string("mlb_debug_fwd_marks: ") + cudaGetErrorString(e);
         return -1;
@@ -734,6 +751,16 @@ extern "C" int mlb_create(const mlb_model_desc* desc, const mlb_op* ops, const f
         m->wide_bar_count = 0;
         CU(cudaDeviceSynchronize());
     }
+    if (ffma_ok && !getenv("MLB_NO_WIDE2") && mlb_wide2_supported(m->ops, desc->n_ops, L, desc->output_size, m->n_sms)) {
+        const size_t wf = mlb_wide2_slab_floats(m->ops, desc->n_ops, L, m->w2slab_off);
+        CU(cudaMalloc(&m->w2slab_dev, wf * sizeof(float)));
+        CU(mlb_wide2_pack(m->blob_dev, m->ops, desc->n_ops, L, m->w2slab_dev, m->w2slab_off, 0));
+        CU(cudaMalloc(&m->wide2_xg, mlb_wide2_xg_pairs(L) * sizeof(unsigned long long)));
+        CU(cudaMemset(m->wide2_xg, 0, mlb_wide2_xg_pairs(L) * sizeof(unsigned long long)));
+        CU(cudaMalloc(&m->wide2_hg, mlb_wide2_hg_pairs(L) * sizeof(unsigned long long)));
+        CU(cudaMemset(m->wide2_hg, 0, mlb_wide2_hg_pairs(L) * sizeof(unsigned long long)));
+        CU(cudaDeviceSynchronize());
+    }
     m->res_floats = (size_t)m->n_sms * 4 * 128 * 256;  // up to 4 resident CTAs per SM for narrow models
     CU(cudaMalloc(&m->res_scratch, m->res_floats * sizeof(float)));
     CU(cudaMalloc(&m->gather_done, sizeof(unsigned)));
@@ -806,6 +833,8 @@ extern "C" int mlb_update_weights(mlb_handle h, const float* packed_host, size_t
         CU(mlb_small_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->slab_dev, h->slab_off, (cudaStream_t)stream));
     if (h->wslab_dev)
         CU(mlb_wide_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->wslab_dev, h->wslab_off, (cudaStream_t)stream));
+    if (h->w2slab_dev)
+        CU(mlb_wide2_pack(h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, h->w2slab_dev, h->w2slab_off, (cudaStream_t)stream));
     if (h->tc) CU(mlb_tc_repack(h->tc, h->blob_dev, h->ops, h->desc.n_ops, h->desc.linear_size, (cudaStream_t)stream));
     return 0;
 }
@@ -818,6 +847,9 @@ extern "C" void mlb_destroy(mlb_handle h) {
     cudaFree(h->wslab_dev);
     cudaFree(h->wide_xg);
     cudaFree(h->wide_bar);
+    cudaFree(h->w2slab_dev);
+    cudaFree(h->wide2_xg);
+    cudaFree(h->wide2_hg);
     cudaFree(h->res_scratch);
     cudaFree(h->gather_done);
     mlb_tc_free(h->tc);
@@ -966,6 +998,31 @@ extern "C" int mlb_forward(mlb_handle h, const mlb_forward_args* a, void* stream
         g_launches++;
         h->last_kernel = MLB_KERNEL_TC;
         return 0;
+    }
+
+    // ---- up to 16 detections (most images): the second-generation latency kernel (forward_wide2.cu): 2-D K x N split in
+    // 4-CTA clusters, partial sums through distributed shared memory, (value, epoch) exchange instead of barrier + copy
+    const bool forced_any = (a->flags & (MLB_FWD_FORCE_TILE | MLB_FWD_FORCE_CLUSTER | MLB_FWD_FORCE_WIDE | MLB_FWD_FORCE_TC)) != 0 ||
+                            a->rows_per_group != 0;
+    if ((a->flags & MLB_FWD_FORCE_WIDE2) && (h->w2slab_dev == nullptr || a->n_rows > 16))
+        return fail("mlb_forward: the second-generation latency kernel needs <= 16 rows and a supported model / device");
+    if (h->w2slab_dev != nullptr && a->n_rows <= 16 && ((a->flags & MLB_FWD_FORCE_WIDE2) || (!forced_any && !h->wide2_disabled))) {
+        p.n_tiles = 1, p.row_base = 0;
+        const unsigned done_before = h->gather_done_count;
+        arm_gather(1u);
+        const unsigned base = h->wide2_epoch;
+        cudaError_t ew = mlb_wide2_launch(p, h->w2slab_dev, h->w2slab_off, h->wide2_xg, h->wide2_hg, base, st);
+        if (ew == cudaSuccess) {
+            h->wide2_epoch = base + (unsigned)mlb_wide2_epochs(h->ops, d.n_ops);
+            g_launches++;
+            h->last_kernel = MLB_KERNEL_WIDE2;
+            return 0;
+        }
+        if (a->flags & MLB_FWD_FORCE_WIDE2) return fail(std::string("loco_forward_wide2_kernel launch: ") + cudaGetErrorString(ew));
+        cudaGetLastError();   // e.g. no cooperative launch under this context: use the other kernels from now on
+        h->wide2_disabled = true;
+        h->gather_done_count = done_before;
+        p.gather_epoch = 0;
     }
 
     // ---- one image's worth of detections: the whole grid on one 32-row tile at a time (forward_wide.cu).  Measured 45 /

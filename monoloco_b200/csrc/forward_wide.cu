@@ -327,7 +327,13 @@ cudaError_t mlb_wide_launch(const FwdParams& p, const float* wslab, const long l
     ex.xg = xg, ex.bar = bar, ex.bar_base = bar_base;
     void* args[] = {(void*)&p, (void*)&ex};
     const int grid = p.L / WC;
-    if (p.n_rows - p.row_base <= 16)
+    // (the opt-in shared-memory size is a per-function, per-process attribute: set it for THIS model's width on every launch)
+    if (p.n_rows - p.row_base <= 16) {
+        cudaError_t e = cudaFuncSetAttribute(loco_forward_wide_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem<16>(p.L));
+        if (e != cudaSuccess) return e;
         return cudaLaunchCooperativeKernel((void*)loco_forward_wide_kernel<16>, dim3(grid), dim3(WNT), args, wide_smem<16>(p.L), st);
+    }
+    cudaError_t e = cudaFuncSetAttribute(loco_forward_wide_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem<32>(p.L));
+    if (e != cudaSuccess) return e;
     return cudaLaunchCooperativeKernel((void*)loco_forward_wide_kernel<32>, dim3(grid), dim3(WNT), args, wide_smem<32>(p.L), st);
 }

@@ -119,7 +119,7 @@ class LocoEngine:
         a.flags = (L_.FWD_ZERO_CENTER if zero_center else 0) | (L_.FWD_DROPOUT if dropout else 0) | \
                   (0 if res_tmem is None else (L_.FWD_RES_TMEM if res_tmem else L_.FWD_RES_SCRATCH)) | \
                   {None: 0, 'tile': L_.FWD_FORCE_TILE, 'cluster': L_.FWD_FORCE_CLUSTER, 'wide': L_.FWD_FORCE_WIDE,
-                   'tc': L_.FWD_FORCE_TC}[kernel]
+                   'tc': L_.FWD_FORCE_TC, 'wide2': L_.FWD_FORCE_WIDE2}[kernel]
         if kind == L_.IN_KPS_STEREO:
             x_right = x_right.contiguous()
             n_left, n_right = x.shape[0], x_right.shape[0]

@@ -57,6 +57,6 @@ def test_header_flag_values_match_python():
     for name, val in (('MLB_FWD_ZERO_CENTER', L_.FWD_ZERO_CENTER), ('MLB_FWD_DROPOUT', L_.FWD_DROPOUT),
                       ('MLB_FWD_RES_TMEM', L_.FWD_RES_TMEM), ('MLB_FWD_FORCE_TILE', L_.FWD_FORCE_TILE),
                       ('MLB_FWD_FORCE_CLUSTER', L_.FWD_FORCE_CLUSTER), ('MLB_FWD_RES_SCRATCH', L_.FWD_RES_SCRATCH),
-                      ('MLB_FWD_FORCE_WIDE', L_.FWD_FORCE_WIDE), ('MLB_FWD_FORCE_TC', L_.FWD_FORCE_TC)):
+                      ('MLB_FWD_FORCE_WIDE', L_.FWD_FORCE_WIDE), ('MLB_FWD_FORCE_TC', L_.FWD_FORCE_TC), ('MLB_FWD_FORCE_WIDE2', L_.FWD_FORCE_WIDE2)):
         m = re.search(name + r'\s*=\s*(\d+)', hdr)
         assert m and int(m.group(1)) == val, name

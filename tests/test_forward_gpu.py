@@ -303,7 +303,7 @@ def test_wide_kernel_batches_vs_oracle(mono1024, B):
         _check_dec(O, out['dec'].cpu().numpy(), O.extract_outputs(ref), False, raw_ref=ref)
     tile = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_xyzc=True, kernel='tile')
     assert torch.allclose(out['raw'], tile['raw'], rtol=2e-5, atol=2e-5) and torch.allclose(out['xyzc'], tile['xyzc'], rtol=1e-5, atol=1e-5)
-    if B <= 64:   # selected by default up to two 32-row tiles (one launch per tile)
+    if 16 < B <= 64:   # selected by default for 17 .. 64 rows (one launch per 32-row tile); <= 16 rows: the wide2 kernel
         auto = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS)
         assert torch.equal(auto['raw'], out['raw'])
 
@@ -347,6 +347,70 @@ def test_wide_kernel_stereo_dropout_and_legacy_models():
     eng = engine.LocoEngine(sd)
     x = synthetic.make_inputs(9, 34, seed=2)
     out = eng.forward(torch.from_numpy(x).cuda(), kernel='wide')
+    ok, worst = O.close(out['raw'].cpu().numpy(), O.monoloco_model_forward(sd, x))
+    assert ok, worst
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ second-generation latency kernel
+@pytest.mark.parametrize('B', [1, 2, 7, 15, 16])
+def test_wide2_kernel_batches_vs_oracle(mono1024, B):
+    """Latency kernel, second generation (forward_wide2.cu): 32 clusters x 4 CTAs, K x N split, partial sums through
+    distributed shared memory, (value, epoch) pair exchange; repeated launches walk the three rotating buffers and the
+    monotonic epochs."""
+    O, synthetic, engine, L_ = _mods()
+    sd, eng = mono1024
+    kps = synthetic.make_keypoints(B, seed=340 + B)
+    x = O.preprocess_monoloco(kps, synthetic.KITTI_K)
+    ref = O.loco_model_forward(sd, x)
+    for rep in range(5):
+        out = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_x=True, want_xyzc=True,
+                          kernel='wide2')
+        assert np.abs(out['x'].cpu().numpy() - x).max() < 6e-6
+        ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+        assert ok, (rep, worst)
+        _check_dec(O, out['dec'].cpu().numpy(), O.extract_outputs(ref), False, raw_ref=ref)
+    tile = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS, want_xyzc=True, kernel='tile')
+    assert torch.allclose(out['raw'], tile['raw'], rtol=2e-5, atol=2e-5) and torch.allclose(out['xyzc'], tile['xyzc'], rtol=1e-5, atol=1e-5)
+    auto = eng.forward(torch.from_numpy(kps).cuda(), kk=synthetic.KITTI_K, kind=L_.IN_KPS)   # the default pick up to 16 rows
+    assert torch.equal(auto['raw'], out['raw']) and eng.last_kernel()[0] == 4
+
+
+def test_wide2_kernel_stereo_dropout_and_legacy_models():
+    O, synthetic, engine, L_ = _mods()
+    f = np.load(os.path.join(GOLDEN, 'ref_loco_stereo.npz'))
+    sd = synthetic.make_state_dict('loco', 68, 10, 1024, 3, 2)
+    eng = engine.LocoEngine(sd)
+    left, right = torch.from_numpy(f['left'][:1]).cuda(), torch.from_numpy(f['right']).cuda()   # 1 x 9 pairs
+    out = eng.forward(left, x_right=right, kk=f['K'], kind=L_.IN_KPS_STEREO, want_x=True, kernel='wide2')
+    n = out['raw'].shape[0]
+    assert n == f['right'].shape[0] and np.abs(out['x'].cpu().numpy() - f['pairs_x'][:n]).max() < 6e-6
+    ok, worst = O.close(out['raw'].cpu().numpy(), f['pairs_raw'][:n])
+    assert ok, worst
+    eng.close()
+    sd = synthetic.make_state_dict('loco', 34, 9, 1024, 3, 0)
+    eng = engine.LocoEngine(sd)
+    B = 13
+    masks = (np.random.RandomState(3).uniform(size=(2, B, 1024)) >= 0.2).astype(np.uint8)
+    x = synthetic.make_inputs(B, 34, seed=31)
+    ref = O.loco_model_forward(sd, x, drop_masks=(masks[0], masks[1]), p_dropout=0.2)
+    out = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_mask=torch.from_numpy(masks).cuda(), kernel='wide2')
+    ok, worst = O.close(out['raw'].cpu().numpy(), ref)
+    assert ok, worst
+    a = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='wide2')['raw']
+    b = eng.forward(torch.from_numpy(x).cuda(), dropout=True, drop_seed=9, kernel='tile')['raw']
+    assert torch.allclose(a, b, rtol=2e-5, atol=2e-5)
+    eng.close()
+    g = np.load(os.path.join(GOLDEN, 'ref_fwd_monoloco_l1024_o9.npz'))
+    eng = engine.LocoEngine(synthetic.make_state_dict('monoloco', 34, 9, 1024, 3, 3))
+    out = eng.forward(torch.from_numpy(g['x'][:16]).cuda(), kernel='wide2')
+    ok, worst = O.close(out['raw'].cpu().numpy(), g['out'][:16])
+    assert ok, worst
+    eng.close()
+    sd = synthetic.make_state_dict('monoloco', 34, 2, 256, 3, 5)   # legacy width: 8 clusters, K slices of 64
+    eng = engine.LocoEngine(sd)
+    x = synthetic.make_inputs(9, 34, seed=2)
+    out = eng.forward(torch.from_numpy(x).cuda(), kernel='wide2')
     ok, worst = O.close(out['raw'].cpu().numpy(), O.monoloco_model_forward(sd, x))
     assert ok, worst
     eng.close()
