@@ -575,8 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) loco_forward_tc_kernel(const __
                 float4* dst = reinterpret_cast<float4*>(p.gather[pg] + (size_t)(p.gather_row0 + (long long)rb * TCM) * MLB_GATHER_LD);
                 for (int i = tid; i < n4; i += TC_THREADS) dst[i] = src[i];
             }
-            __threadfence_system();  // peer stores ordered before this CTA's arrival in gather_finish()
-            __syncthreads();
+            __syncthreads();   // peer stores ordered before this CTA's arrival in gather_finish() (barrier + its fence)
         }
         // the next tile's prologue ends with a cluster barrier: CTA 0 has finished reading hpart before any peer writes it
         // again, and before its own producer refills the ring that hpart aliases (program order + fence.proxy.async)

@@ -38,14 +38,16 @@ struct FwdParams {
 
 enum { ERR_GATHER_TIMEOUT = 4 };
 
-// Called by ONE thread of every CTA that stored gather rows, after a CTA barrier that follows those stores (each storing
-// thread has executed __threadfence_system() after its last store).  The last CTA to arrive publishes this rank's epoch
+// Called by ONE thread of every CTA that stored gather rows, after a CTA barrier that follows those stores.  No per-thread
+// fence is needed (one fence.sc.sys per storing thread cost 20 us per launch): the barrier orders the CTA's stores before
+// this thread, its gpu-scope fence + arrival (release pattern) and the last arriver's system-scope fence + st.release.sys
+// are cumulative over everything observed before them.  The last CTA to arrive publishes this rank's epoch
 // into every rank's flag array (release at system scope: cumulativity orders all CTAs' peer stores before the flag) and
 // then waits until every rank's epoch has reached this rank's own array -- the kernel retires only when the whole
 // gathered buffer is complete here.  Bounded by %globaltimer (20 s): a dead peer raises the error flag instead of hanging.
 __device__ __forceinline__ void gather_finish(const FwdParams& p) {
     if (p.n_gather == 0 || p.gather_epoch == 0) return;
-    __threadfence();
+    __threadfence();   // gpu scope is enough for the CTA -> last-arriver edge; the last arriver fences at system scope
     const unsigned prev = atomicAdd(p.gather_done, 1u);
     if (prev + 1u != p.gather_done_target) return;
     __threadfence_system();
@@ -200,7 +202,6 @@ __device__ __forceinline__ void store_row(const FwdParams& p, size_t grow, const
         reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[0] = make_float4(x, y, z, d);
         reinterpret_cast<float4*>(dst + MLB_GATHER_DEC)[1] = make_float4(bi, yaw_p, yaw_o, aux);
     }
-    if (p.n_gather) __threadfence_system();  // peer stores ordered before this CTA's arrival in gather_finish()
     if (p.out_xyzc != nullptr && p.input_kind != MLB_IN_X) {
         // net.py:195,213: xy_centers = pixel_to_camera(uv_centers, kk, 1); xyz_from_distance(d, centre)
         const float uc = cen_row[0], vc = cen_row[1];
