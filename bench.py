@@ -431,6 +431,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+        # the sampler start-up + barrier left the GPU idle for ~0.2 s: two more untimed steps, queued directly in front of the
+        # timed ones, so that step 0 is not billed for the wake-up (it was 1.5 x the median in every run)
+        for _ in range(2):
+            flush.zero_()
+            step()
         launches0 = lib.mlb_launch_count()
         for e0, e1 in ev:
             flush.zero_()
