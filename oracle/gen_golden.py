@@ -138,6 +138,30 @@ def ref_forward():
         print('fwd', name, out.shape, float(out.abs().mean()))
 
 
+def ref_forward_wide():
+    """`--hidden_size` values outside the reference's default (run.py:101,122; hyp_tuning.py:52 searches 2048): the real
+    nn.Module at the widest width the kernels cover and at widths the packer has to pad.  Written as ref_wide_*.npz so
+    that the ref_fwd_* parametrisations stay as they were."""
+    cfgs = [
+        # name, kind, in, out, L, stages, seed, n_rows
+        ('loco_mono_l2048', 'loco', 34, 9, 2048, 3, 21, 150),
+        ('loco_stereo_l2048', 'loco', 68, 10, 2048, 3, 22, 64),
+        ('loco_mono_l1500_s1', 'loco', 34, 9, 1500, 1, 23, 90),
+        ('loco_stereo_l300_s2', 'loco', 68, 10, 300, 2, 24, 70),
+        ('monoloco_l200_o9', 'monoloco', 34, 9, 200, 3, 25, 50),
+    ]
+    for name, kind, isz, osz, L, st, seed, n in cfgs:
+        model, sd = build(kind, isz, osz, L, st, seed)
+        x = synthetic.make_inputs(n, isz, seed=100 + seed)
+        with torch.no_grad():
+            out = model(torch.from_numpy(x))
+        save = dict(x=x, out=out.numpy(), cfg=np.array([isz, osz, L, st, seed]), kind=kind, checksum=sd_checksum(sd))
+        dec = extract_outputs(out) if kind == 'loco' else extract_outputs_mono(out)
+        save.update(dic_to_np(dec, 'dec_'))
+        np.savez_compressed(os.path.join(OUT, 'ref_wide_%s.npz' % name), **save)
+        print('wide', name, out.shape, float(out.abs().mean()))
+
+
 def ref_loco_forward():
     """Full Loco.forward (pre + model + post) on the reference's pifpaf fixture (mono) and on the
     stereo fixture's left/right keypoints (stereo, all-vs-all + filter)."""
@@ -354,7 +378,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     steps = {'kat': kat_preprocess, 'forward': ref_forward, 'loco': ref_loco_forward, 'losses': ref_losses,
              'epistemic': ref_epistemic, 'api': ref_api, 'dataset': ref_dataset_order, 'kitti': ref_kitti_txt,
-             'activity': ref_activity}
+             'activity': ref_activity, 'wide': ref_forward_wide}
     for name in (sys.argv[1:] or list(steps)):   # python oracle/gen_golden.py [step ...]
         steps[name]()
     print('done')

@@ -176,3 +176,67 @@ def test_model_copy_and_pickle_drop_the_engine_handle():
     r = torch.load(buf, weights_only=False)
     assert r._engine is None and sorted(r.state_dict()) == sorted(m.state_dict())
     assert m._engine.value == 1234   # the original keeps its handle
+
+
+def _run_packed_program(pm, x):
+    """Host interpreter of the packed layer program (include/monoloco_b200.h `mlb_op`), fp64: what every fused forward
+    kernel executes, minus dropout.  Used only to check that the packer's layout / BN folding / width padding keep the
+    reference's arithmetic; the kernels themselves are checked on the GPU."""
+    from monoloco_b200 import _lib as L_
+    L = pm.desc['linear_size']
+    blob = pm.blob.astype(np.float64)
+    cur, res = None, None
+    out = np.zeros((x.shape[0], pm.desc['output_size']))
+    for o in pm.ops:
+        if o['type'] == L_.OP_GEMM:
+            src = x if o['flags'] & L_.F_IN_XIN else cur
+            wt = blob[o['w_off']:o['w_off'] + o['Kpad'] * L].reshape(o['Kpad'], L)
+            y = src @ wt[:src.shape[1]]
+            y = y * blob[o['scale_off']:o['scale_off'] + L] + blob[o['shift_off']:o['shift_off'] + L]
+            if o['flags'] & L_.F_RELU:
+                y = np.maximum(y, 0)
+            if o['flags'] & L_.F_ADD_RES:
+                y = y + res
+            if o['flags'] & L_.F_SAVE_RES:
+                res = y
+            cur = y
+        else:
+            w = blob[o['w_off']:o['w_off'] + o['N'] * L].reshape(o['N'], L)
+            out[:, o['out_col']:o['out_col'] + o['N']] = cur @ w.T + blob[o['shift_off']:o['shift_off'] + o['N']]
+    return out, cur
+
+
+@pytest.mark.parametrize('kind,width,n_out,stages', [('loco', 256, 9, 3), ('loco', 300, 10, 2), ('loco', 1100, 9, 1),
+                                                     ('monoloco', 200, 9, 3), ('monoloco', 128, 2, 0)])
+def test_packed_program_matches_oracle_any_width(kind, width, n_out, stages):
+    """The packed program reproduces the reference network (oracle restatement of architectures.py:8-46, 111-133) for
+    hidden widths that need padding too: padded units carry exact zeros through every layer."""
+    from monoloco_b200 import synthetic, packing
+    from oracle import loco_oracle as O
+    n_in = 68 if kind == 'loco' else 34
+    sd = synthetic.make_state_dict(kind, n_in, n_out, width, stages, seed=width)
+    pm = packing.pack_state_dict(sd)
+    Lp = packing.padded_width(width)
+    assert pm.desc['linear_size'] == Lp and Lp % 128 == 0 and Lp >= width
+    x = np.random.RandomState(1).randn(37, n_in).astype(np.float32)
+    got, hidden = _run_packed_program(pm, x.astype(np.float64))
+    ref = O.model_forward({k: np.asarray(v, dtype=np.float64) for k, v in sd.items()}, x.astype(np.float64))
+    assert got.shape == ref.shape
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-5), np.abs(got - ref).max()
+    assert not hidden[:, width:].any()          # padded hidden units are exactly zero
+
+
+def test_packed_program_matches_live_reference_wide():
+    """Same interpreter against the live-reference fixtures of the padded widths (tests/golden/ref_wide_*.npz)."""
+    import glob
+    from monoloco_b200 import synthetic, packing
+    from oracle import loco_oracle as O
+    paths = sorted(glob.glob(os.path.join(GOLDEN, 'ref_wide_*.npz')))
+    assert len(paths) >= 5
+    for path in paths:
+        f = np.load(path)
+        isz, osz, L, st, seed = [int(v) for v in f['cfg'][:5]]
+        pm = packing.pack_state_dict(synthetic.make_state_dict(str(f['kind']), isz, osz, L, st, seed))
+        got, _ = _run_packed_program(pm, f['x'].astype(np.float64))
+        ok, worst = O.close(got, f['out'])
+        assert ok, (path, worst)

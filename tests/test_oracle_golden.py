@@ -48,8 +48,10 @@ def test_pixel_to_camera_linearity():
     assert np.allclose(a, b, rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'ref_fwd_*.npz'))))
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'ref_fwd_*.npz')) + glob.glob(os.path.join(GOLDEN, 'ref_wide_*.npz'))))
 def test_forward_vs_reference(path):
+    """The oracle's network against the real nn.Module: the default widths (ref_fwd_*) and the widths outside the default
+    that `--hidden_size` allows (ref_wide_*: 2048, 1500, 300, 200)."""
     f = np.load(path)
     sd = _sd(f)
     out = O.model_forward(sd, f['x'])
