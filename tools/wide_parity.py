@@ -2,7 +2,7 @@
 fixtures tests/golden/ref_wide_*.npz (oracle/gen_golden.py `wide`): prints err / tolerance of the raw outputs per fixture
 and kernel, plus the same against the fp64 oracle on a larger synthetic batch.  GPU box only.
 
-    python tools/wide_parity.py [out.json]
+    python tools/wide_parity.py [out.json [substring of the fixture names to run]]
 """
 import glob
 import json
@@ -20,7 +20,10 @@ from oracle import loco_oracle as O  # noqa: E402  (checker only)
 
 def main():
     rows = []
-    for path in sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'ref_wide_*.npz'))):
+    only = sys.argv[2] if len(sys.argv) > 2 else ''
+    for path in sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'ref_wide_*.npz')), reverse=True):
+        if only not in os.path.basename(path):
+            continue
         f = np.load(path)
         isz, osz, L, st, seed = [int(v) for v in f['cfg'][:5]]
         kind = str(f['kind'])
